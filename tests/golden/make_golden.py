@@ -1,0 +1,294 @@
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py            # writes ops.pt, path_{eb4,r18,r50}.pt
+
+The reference has no tests or golden vectors of its own, so these fixtures are
+the parity pin: inputs + outputs (+ gradients) of the reference's own modules / model classes
+on seeded inputs.  Weights are regenerated from their state_dict names (procedural.py) so the
+files stay small.  Nothing is copied from the reference; it is imported and executed.
+"""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import procedural as P          # noqa: E402
+import ref_loader               # noqa: E402
+
+
+def T(name, shape, kind="unit"):
+    return P.tensor_for("in:" + name, shape, kind)
+
+
+def grads_of(loss, tensors):
+    gs = torch.autograd.grad(loss, tensors, allow_unused=True)
+    return [None if g is None else g.detach().clone() for g in gs]
+
+
+# --------------------------------------------------------------------------------------
+def make_ops(ref):
+    out = {}
+    M = ref.modules
+    Swish = ref.efficientnet.MemoryEfficientSwish
+
+    # --- interpolate (model/unidefense.py:16) ---
+    cases = []
+    for name, shp, size in [("up", (2, 3, 5, 6), (11, 12)), ("up2", (1, 3, 96, 96), (190, 190)),
+                            ("down", (2, 3, 19, 19), (4, 4)), ("down2", (2, 3, 38, 38), (3, 5)),
+                            ("same", (1, 2, 7, 7), (7, 7))]:
+        x = T("interp_" + name, shp)
+        cases.append({"x": x, "size": size, "y": ref.unidefense.interpolate(x, size=size)})
+    out["interpolate"] = cases
+
+    # --- swish + instance norm epilogues ---
+    cases = []
+    for name, shp, act in [("a", (2, 4, 6, 5), "swish"), ("b", (3, 5, 7, 7), "relu"), ("c", (1, 3, 12, 12), "swish")]:
+        x = T("inact_x_" + name, shp, "normal").requires_grad_()
+        inorm = nn.InstanceNorm2d(shp[1], affine=True)
+        with torch.no_grad():
+            inorm.weight.copy_(P.tensor_for("inact_g_" + name, (shp[1],), "gamma"))
+            inorm.bias.copy_(P.tensor_for("inact_b_" + name, (shp[1],), "beta"))
+        a = Swish() if act == "swish" else nn.ReLU()
+        y = a(inorm(x))
+        gy = T("inact_gy_" + name, shp, "normal")
+        gx, gg, gb = grads_of((y * gy).sum(), [x, inorm.weight, inorm.bias])
+        cases.append({"x": x.detach(), "gamma": inorm.weight.detach().clone(), "beta": inorm.bias.detach().clone(),
+                      "act": act, "y": y.detach(), "gy": gy, "gx": gx, "ggamma": gg, "gbeta": gb})
+    out["in_act"] = cases
+
+    # --- dynamic filters (model/modules.py:79-134) ---
+    cases = []
+    for kind, C, h, w, act, N in [("freq", 6, 5, 3, "swish", 3), ("freq", 4, 4, 3, "relu", 2),
+                                  ("spat", 5, 6, 6, "swish", 3), ("spat", 8, 4, 5, "relu", 2)]:
+        A = Swish if act == "swish" else nn.ReLU
+        if kind == "freq":
+            mod = M.FrequencyDynamicFilter(C, A, nn.BatchNorm2d, True, False)
+            cin, cd = 2 * C, 6
+        else:
+            mod = M.SpatialDynamicFilter(C, A, nn.BatchNorm2d, True, False)
+            cin, cd = C, 3
+        tag = f"dyfi_{kind}_{C}_{act}"
+        P.fill_state_dict_(mod, salt=1)
+        sd0 = {k: v.clone() for k, v in mod.state_dict().items()}
+        x = T(tag + "_x", (N, cin, h, w), "normal").requires_grad_()
+        diff = T(tag + "_d", (N, cd, h, w), "unit").abs()
+        mod.train()
+        o = mod(x, diff)
+        gm = T(tag + "_gm", o["mask"].shape, "normal")
+        go = T(tag + "_go", o["out"].shape, "normal")
+        params = [mod.layer1[0].weight, mod.layer1[1].weight, mod.layer1[1].bias, mod.layer2[0].weight]
+        gs = grads_of((o["mask"] * gm).sum() + (o["out"] * go).sum(), [x] + params)
+        sd1 = {k: v.clone() for k, v in mod.state_dict().items()}
+        mod.eval()
+        with torch.no_grad():
+            oe = mod(x, diff)
+        cases.append({"kind": kind, "C": C, "act": act, "x": x.detach(), "diff": diff, "sd0": sd0, "sd1": sd1,
+                      "mask": o["mask"].detach(), "out": o["out"].detach(), "gm": gm, "go": go,
+                      "gx": gs[0], "gw1": gs[1], "ggamma": gs[2], "gbeta": gs[3], "gw2": gs[4],
+                      "mask_eval": oe["mask"], "out_eval": oe["out"]})
+    out["dyfi"] = cases
+
+    # --- losses (loss/) ---
+    tri = ref.loss.LOSSES["aw_triplet"]
+    cases = []
+    for name, N, nr, c in [("a", 4, 2, 16), ("b", 8, 4, 40), ("c", 6, 2, 7), ("d", 20, 10, 160), ("e", 5, 3, 3)]:
+        f = T("tri_" + name, (N, c), "normal").requires_grad_()
+        lab = torch.tensor([0] * nr + [1] * (N - nr), dtype=torch.int64)
+        l = tri(f, lab)
+        (g,) = grads_of(l, [f])
+        cases.append({"feat": f.detach(), "labels": lab, "loss": l.detach(), "gfeat": g})
+    # near-duplicate rows exercise clamp(min=1e-12).sqrt()
+    f = T("tri_dup", (4, 8), "normal")
+    f[1] = f[0]
+    f = f.requires_grad_()
+    lab = torch.tensor([0, 0, 1, 1])
+    l = tri(f, lab)
+    (g,) = grads_of(l, [f])
+    cases.append({"feat": f.detach(), "labels": lab, "loss": l.detach(), "gfeat": g})
+    out["triplet"] = cases
+
+    fac = ref.loss.LOSSES["factorization"]
+    cases = []
+    for name, N, Fd in [("a", 4, 16), ("b", 8, 40), ("c", 20, 96), ("d", 2, 5)]:
+        a = T("fac_a_" + name, (N, Fd), "normal").requires_grad_()
+        b = T("fac_b_" + name, (N, Fd), "normal")
+        l = fac(a, b)
+        (g,) = grads_of(l, [a])
+        cases.append({"a": a.detach(), "b": b, "loss": l.detach(), "ga": g})
+    out["factorization"] = cases
+
+    kl = ref.loss.LOSSES["kl_div"]
+    cases = []
+    for name, shp in [("a", (4, 1, 5, 3)), ("b", (6, 1, 12, 7))]:
+        p = torch.sigmoid(T("kl_p_" + name, shp, "normal")).requires_grad_()
+        gt = torch.sigmoid(T("kl_g_" + name, shp, "normal"))
+        # engine/abstract_engine.py:333-337
+        l = kl(torch.log_softmax(p.reshape(shp[0], -1), dim=-1), torch.log_softmax(gt.reshape(shp[0], -1), dim=-1))
+        (g,) = grads_of(l, [p])
+        cases.append({"pred": p.detach(), "gt": gt, "loss": l.detach(), "gpred": g})
+    out["mask_kl"] = cases
+
+    # --- perturbations ---
+    cases = []
+    fst = M.FrequencyStyleTransfer()
+    for name, shp in [("a", (2, 3, 12, 10)), ("b", (2, 3, 9, 7)), ("c", (1, 3, 20, 19))]:
+        c_, s_ = T("fst_c_" + name, shp), T("fst_s_" + name, shp)
+        torch.manual_seed(11)
+        lm = torch.rand((shp[0], 1, 1, 1)) / 2.0 + 0.5
+        torch.manual_seed(11)
+        y = fst(c_, s_)
+        cases.append({"content": c_, "style": s_, "lmda": lm, "y": y})
+    out["freq_style"] = cases
+
+    cases = []
+    sst = M.SpatialStyleTransfer()
+    for name, shp in [("a", (2, 3, 8, 8)), ("b", (3, 3, 7, 5))]:
+        c_, s_ = T("sst_c_" + name, shp), T("sst_s_" + name, shp)
+        torch.manual_seed(12)
+        lm = torch.rand((shp[0], 1, 1)) / 2.0 + 0.5
+        torch.manual_seed(12)
+        y = sst(c_, s_)
+        cases.append({"content": c_, "style": s_, "lmda": lm, "y": y})
+    out["spat_style"] = cases
+
+    cases = []
+    for name, shp in [("a", (3, 8, 8)), ("b", (3, 12, 9)), ("c", (3, 20, 20))]:
+        s_, t_ = T("coral_s_" + name, shp), T("coral_t_" + name, shp) * 0.5 + 0.1
+        cases.append({"source": s_, "target": t_, "y": ref.operation.coral(s_, t_)})
+    out["coral"] = cases
+
+    cases = []
+    for name, shp in [("a", (2, 3, 9, 11)), ("b", (1, 3, 20, 20))]:
+        x = T("blur_" + name, shp)
+        cases.append({"x": x, "y": M.random_blur(x)})
+    out["blur"] = cases
+    cases = []
+    for name, shp in [("a", (2, 3, 10, 10)), ("b", (1, 3, 13, 9)), ("c", (1, 3, 38, 38)), ("d", (1, 3, 75, 64))]:
+        x = T("ds_" + name, shp)
+        cases.append({"x": x, "y": M.downscale(x)})
+    out["downscale"] = cases
+
+    # --- SFConv frequency branch (a17, secondary) ---
+    cases = []
+    from model.efficientnet.exp import SFConv2dStaticSamePadding   # resolved inside the reference tree
+    from model.resnet.exp import SFConv2d
+    for name, kind, C, hw, stride, norm in [("e1", "eff", 4, 12, 1, "ortho"), ("e2", "eff", 6, 9, 2, "ortho"),
+                                            ("r1", "res", 4, 8, 1, "ortho"), ("r2", "res", 4, 8, 2, None)]:
+        if kind == "eff":
+            m = SFConv2dStaticSamePadding(C, C, 3, stride=stride, image_size=hw, freq_norm=norm, groups=C, bias=False)
+        else:
+            m = SFConv2d(C, C, 3, stride=stride, padding=1, bias=False, freq_norm=norm)
+        P.fill_state_dict_(m, salt=2)
+        with torch.no_grad():
+            m.sf_coef.fill_(0.2)
+        x = T("sf_" + name, (2, C, hw, hw), "normal").requires_grad_()
+        y = m(x)
+        gy = T("sf_gy_" + name, y.shape, "normal")
+        gx, gw = grads_of((y * gy).sum(), [x, m.freq_conv.weight])
+        cases.append({"kind": kind, "stride": stride, "norm": norm, "x": x.detach(), "y": y.detach(), "gy": gy,
+                      "gx": gx, "gfw": gw, "sd": {k: v.clone() for k, v in m.state_dict().items()}})
+    out["sfconv"] = cases
+    return out
+
+
+# --------------------------------------------------------------------------------------
+def make_path(ref, arch):
+    """Run the reference MODEL CLASS in train mode (dropout off) and capture every tensor that
+    crosses the hot-path boundary, plus gradients of a fixed hot-path loss."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    if arch == "eb4":
+        model = ref.unidefense.UniDefenseModelEb4("efficientnet-b4", num_classes=2, drop_rate=0.0)
+        R, N = 128, 4
+    elif arch == "r18":
+        model = ref.unidefense.UniDefenseModelRes18(drop_rate=0.0)
+        R, N = 76, 4
+    else:
+        model = ref.unidefense.UniDefenseModelRes50(drop_rate=0.0)
+        R, N = 64, 4
+    P.fill_state_dict_(model, prefix_filter=P.is_hot, salt=3)
+    # make the SFConv branches numerically live inside the backbone (init -10 hides them)
+    with torch.no_grad():
+        for n_, p_ in model.named_parameters():
+            if n_.endswith("sf_coef"):
+                p_.fill_(0.0)
+    model.train()
+    cap = {}
+
+    def pre_hook(mod, args):
+        args[0].retain_grad()
+        cap["feat"] = args[0]
+
+    model.dec_block1.register_forward_pre_hook(pre_hook)
+    nblocks = 3 if arch != "r18" else 2
+    for i in range(1, nblocks + 1):
+        getattr(model, f"dec_block{i}").register_forward_hook(
+            lambda m, a, o, i=i: cap.__setitem__(f"dec_out{i}", o))
+    orig_att = model.attention
+
+    def att(pred, x, emb):
+        emb.retain_grad()
+        cap["att_pred"], cap["emb"] = pred, emb
+        o = orig_att(pred, x, emb)
+        cap["att_out"] = o["out"]
+        return o
+
+    model.attention = att
+    x = T(f"path_x_{arch}", (N, 3, R, R))
+    labels = torch.tensor([0] * (N // 2) + [1] * (N // 2))
+    # identity decoder-input dropout (F.dropout p=0.2 is hard-coded, unidefense.py:213/393/586)
+    orig_dropout = F.dropout
+    F.dropout = lambda t, p=0.5, training=True, inplace=False: t * 1.0   # new node: grad = decoder path only
+    try:
+        out = model(x)
+    finally:
+        F.dropout = orig_dropout
+    ld = out["loss_dict"]
+    nr = N // 2
+    tri = ref.loss.LOSSES["aw_triplet"]
+    r_att = P.tensor_for(f"path_ratt_{arch}", cap["att_out"].shape, "normal")
+    tri_loss = sum(tri(f, labels) for f in ld["triplet"])
+    loss = (0.1 * ld["freq_mask"].mean() + 0.1 * ld["spat_mask"].mean() + 0.1 * tri_loss
+            + 0.1 * ld["spatial"][:nr].mean() + 1.0 * ld["freq"][:nr].mean() + (cap["att_out"] * r_att).sum())
+    hot = [(n_, p_) for n_, p_ in model.named_parameters() if P.is_hot(n_) and p_.requires_grad
+           and not n_.startswith(("bottleneck", "classifier"))]
+    gs = torch.autograd.grad(loss, [cap["feat"], cap["emb"]] + [p_ for _, p_ in hot], allow_unused=True)
+    pg = {}
+    for (n_, p_), g in zip(hot, gs[2:]):
+        idx = P.sample_indices(p_.numel(), 64, n_)
+        pg[n_] = {"norm": g.norm().item(), "sum": g.sum().item(), "sample": g.flatten()[idx].clone()}
+    fix = {"arch": arch, "R": R, "N": N, "x": x, "labels": labels,
+           "feat": cap["feat"].detach(), "emb": cap["emb"].detach(), "att_pred": cap["att_pred"].detach(),
+           "att_out": cap["att_out"].detach(), "r_att": r_att,
+           "rec": out["rec"].detach(), "spatial": ld["spatial"].detach(), "freq": ld["freq"].detach(),
+           "freq_mask": ld["freq_mask"].detach(), "spat_mask": ld["spat_mask"].detach(),
+           "triplet_feats": [t.detach() for t in ld["triplet"]], "triplet_loss": tri_loss.detach(),
+           "loss": loss.detach(), "g_feat": gs[0].detach(), "g_emb": gs[1].detach(), "param_grads": pg,
+           "bn_after": {k: v.clone() for k, v in model.state_dict().items()
+                        if k.startswith(("freq_filter.layer1.1.running", "spat_filter.layer1.1.running"))}}
+    for i in range(1, nblocks + 1):
+        fix[f"dec_out{i}"] = cap[f"dec_out{i}"].detach()
+    # store big activations in fp16-free form but trimmed: keep everything fp32 (files stay < 2 MB each)
+    return fix
+
+
+def main():
+    ref = ref_loader.load()
+    which = sys.argv[1:] or ["ops", "eb4", "r18", "r50"]
+    if "ops" in which:
+        torch.save(make_ops(ref), os.path.join(HERE, "ops.pt"))
+        print("wrote ops.pt", os.path.getsize(os.path.join(HERE, "ops.pt")))
+    for arch in ("eb4", "r18", "r50"):
+        if arch in which:
+            fn = os.path.join(HERE, f"path_{arch}.pt")
+            torch.save(make_path(ref, arch), fn)
+            print("wrote", fn, os.path.getsize(fn))
+
+
+if __name__ == "__main__":
+    main()
