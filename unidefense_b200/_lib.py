@@ -1,0 +1,91 @@
+"""ctypes binding of libunidefense_b200.so (the C ABI declared in include/unidefense_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing, or a tensor is not
+a contiguous CUDA fp32 tensor, the call fails loudly.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libunidefense_b200.so")
+_lib = None
+_lock = threading.Lock()
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_f = ctypes.c_float
+c_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/unidefense_b200.h declares
+SIGNATURES = {
+    "ud_last_error": (ctypes.c_char_p, []),
+    "ud_version": (c_i, []),
+    "ud_fft_size_supported": (c_i, [c_i]),
+    "ud_recon_tail_workspace_bytes": (c_sz, [c_i] * 6),
+    "ud_recon_tail_signs_bytes": (c_sz, [c_i] * 4),
+    "ud_recon_tail_fwd": (c_i, [c_p] * 7 + [c_sz] + [c_i] * 7 + [c_p]),
+    "ud_recon_tail_bwd": (c_i, [c_p] * 7 + [c_sz] + [c_i] * 7 + [c_p]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                        "(or `make -C unidefense_b200/csrc`). There is no CPU/PyTorch fallback.")
+                L = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(L, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().ud_last_error().decode(errors="replace")
+        raise RuntimeError(f"unidefense_b200 {what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda_f32(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("unidefense_b200 kernels need CUDA tensors (no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"unidefense_b200 kernels are fp32; got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError("unidefense_b200 kernels need contiguous tensors")
+
+
+_ws = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only byte workspace per (device, stream); safe because every kernel that uses it
+    is enqueued on that same stream."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream())
+    t = _ws.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = t
+    return t

@@ -1,0 +1,133 @@
+// Library-wide state for libunidefense_b200.so: thread-local error string, version, the
+// per-(device, n) twiddle-table cache and FFT plan factorisation.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "../../include/unidefense_b200.h"
+#include "ud_fft.cuh"
+
+static thread_local char g_err[512] = "";
+
+void ud_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ud_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ud_set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+    return UD_ERR_CUDA;
+  }
+  return UD_OK;
+}
+
+extern "C" const char* ud_last_error(void) { return g_err; }
+extern "C" int ud_version(void) { return UD_B200_VERSION; }
+
+bool ud_make_dyn_plan(int n, UdDynPlan* plan) {
+  if (n < 1) return false;
+  static const int primes[] = {23, 19, 17, 13, 11, 7, 5, 3};
+  plan->n_ = n;
+  plan->nstages = 0;
+  int m = n;
+  for (int p : primes) {
+    while (m % p == 0) {
+      if (plan->nstages >= UD_FFT_MAX_STAGES) return false;
+      plan->radix[plan->nstages++] = p;
+      m /= p;
+    }
+  }
+  while (m % 4 == 0) {
+    if (plan->nstages >= UD_FFT_MAX_STAGES) return false;
+    plan->radix[plan->nstages++] = 4;
+    m /= 4;
+  }
+  if (m % 2 == 0) {
+    if (plan->nstages >= UD_FFT_MAX_STAGES) return false;
+    plan->radix[plan->nstages++] = 2;
+    m /= 2;
+  }
+  return m == 1;
+}
+
+extern "C" int ud_fft_size_supported(int n) {
+  UdDynPlan p;
+  return (n >= 1 && n <= UD_FFT_MAX_N && ud_make_dyn_plan(n, &p)) ? 1 : 0;
+}
+
+// exp(-2 pi i t / n) with exact octant symmetry (so W^(n/4), W^(n/2) ... are exact)
+static void twiddle_host(int n, std::vector<float2>& out) {
+  out.resize(n);
+  for (int t = 0; t < n; ++t) {
+    // reduce the angle 2 pi t/n to the first octant using integer arithmetic on 8t/n
+    long long num = (long long)t * 8;  // angle = (num/n) * pi/4
+    int oct = (int)(num / n);
+    long long rem = num - (long long)oct * n;  // in [0, n): fraction of an octant
+    double c, s;
+    if ((oct & 1) == 0) {
+      double a = (double)rem / (double)n * (M_PI / 4.0);
+      c = cos(a);
+      s = sin(a);
+    } else {
+      double a = (double)(n - rem) / (double)n * (M_PI / 4.0);
+      c = sin(a);
+      s = cos(a);
+    }
+    // now (c,s) = (cos, sin) of the angle folded into [0, pi/2) for quadrant oct/2
+    double cr, sr;
+    switch ((oct >> 1) & 3) {
+      case 0: cr = c; sr = s; break;
+      case 1: cr = -s; sr = c; break;
+      case 2: cr = -c; sr = -s; break;
+      default: cr = s; sr = -c; break;
+    }
+    if (rem == 0) {  // exact multiples of pi/4: kill rounding residue on the axes
+      if ((oct & 1) == 0) {
+        const double ex[4][2] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
+        cr = ex[(oct >> 1) & 3][0];
+        sr = ex[(oct >> 1) & 3][1];
+      }
+    }
+    out[t] = make_float2((float)cr, (float)(-sr));
+  }
+}
+
+static std::mutex g_tw_mutex;
+static std::map<std::pair<int, int>, float2*> g_tw_cache;
+
+const float2* ud_twiddles(int n) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    ud_set_error("cudaGetDevice failed");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(g_tw_mutex);
+  auto key = std::make_pair(dev, n);
+  auto it = g_tw_cache.find(key);
+  if (it != g_tw_cache.end()) return it->second;
+  std::vector<float2> h;
+  twiddle_host(n, h);
+  float2* d = nullptr;
+  if (cudaMalloc(&d, sizeof(float2) * (size_t)n) != cudaSuccess) {
+    ud_set_error("cudaMalloc(twiddles n=%d) failed", n);
+    return nullptr;
+  }
+  // synchronous copy on the legacy stream: tables are immutable afterwards, and any stream
+  // that later reads them is ordered after this call returns.
+  if (cudaMemcpy(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
+    ud_set_error("cudaMemcpy(twiddles n=%d) failed", n);
+    cudaFree(d);
+    return nullptr;
+  }
+  g_tw_cache[key] = d;
+  return d;
+}
