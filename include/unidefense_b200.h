@@ -68,6 +68,96 @@ UD_API int ud_recon_tail_bwd(const float* dec, const float* x, const uint8_t* si
                              const float* g_freq, float* g_dec, void* ws, size_t ws_bytes, int N, int C, int h,
                              int w, int H, int W, int norm_ortho, cudaStream_t stream);
 
+/* ---- a2: decoder epilogues ------------------------------------------------------------------
+ * nn.InstanceNorm2d(C, affine) + MemoryEfficientSwish / nn.ReLU after every decoder conv
+ * (model/unidefense.py:61-98, :286-305, :466-497): x [N,C,HW] -> y = act((x-mu)/sqrt(var+eps)*gamma+beta)
+ * per (n,c) plane, biased variance, no running stats.  mean/rstd [N*C] are saved for backward.
+ * ymean (nullable) [N*C] receives mean_hw(y): the triplet features dec_out.mean([-2,-1])
+ * (model/unidefense.py:232-236) for free.  gamma/beta may be NULL (affine=False).              */
+UD_API int ud_in_act_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                         float* rstd, float* ymean, int N, int C, int HW, float eps, int act,
+                         cudaStream_t stream);
+UD_API size_t ud_in_act_bwd_workspace_bytes(int N, int C);
+/* gx [N,C,HW], ggamma/gbeta [C] (nullable).  g_ymean (nullable) [N*C] is the gradient w.r.t. ymean.
+ * Swish backward follows SwishImplementation.backward (model/efficientnet/utils.py:73-77).       */
+UD_API int ud_in_act_bwd(const float* x, const float* gy, const float* gamma, const float* beta,
+                         const float* mean, const float* rstd, const float* g_ymean, float* gx, float* ggamma,
+                         float* gbeta, void* ws, size_t ws_bytes, int N, int C, int HW, int act,
+                         cudaStream_t stream);
+/* nn.Tanh decoder output (model/unidefense.py:101, :307, :499). */
+UD_API int ud_tanh_fwd(const float* x, float* y, long long n, cudaStream_t stream);
+UD_API int ud_tanh_bwd(const float* y, const float* gy, float* gx, long long n, cudaStream_t stream);
+
+/* ---- a4 / a7: attention() glue -----------------------------------------------------------------
+ * F.interpolate(mode='bilinear', align_corners=True) (model/unidefense.py:16) on [planes,h,w] -> [planes,H,W]
+ * and its transpose (upsample_bilinear2d_backward; gx is zeroed by the call).                       */
+UD_API int ud_bilinear_ac_fwd(const float* x, float* y, int planes, int h, int w, int H, int W, cudaStream_t stream);
+UD_API int ud_bilinear_ac_bwd(const float* gy, float* gx, int planes, int h, int w, int H, int W,
+                              cudaStream_t stream);
+/* Error maps (model/unidefense.py:126-134,:148; no grad): pred [N,C,hp,wp] and x [N,C,Hx,Wx] are resized
+ * to (h,w); spat_diff [N,C,h,w] = |p-xs|; freq_diff [N,2C,h,w/2+1] = |cat(re,im) rfft2(p-xs)|.      */
+UD_API int ud_attn_prep(const float* pred, const float* x, float* spat_diff, float* freq_diff, int N, int C, int hp,
+                        int wp, int Hx, int Wx, int h, int w, int norm_ortho, cudaStream_t stream);
+/* torch.fft.rfft2 + cat([re,im],1) of feature maps (model/unidefense.py:135-136): x [N,C,h,w] ->
+ * xf [N,2C,h,w/2+1]; h,w <= 64.  adjoint_of_inverse=1 gives irfft2's backward (fft_c2r_backward:
+ * interior columns doubled, inverse normalisation).                               */
+UD_API int ud_rfft2_cat(const float* x, float* xf, int N, int C, int h, int w, int norm_ortho,
+                        int adjoint_of_inverse, cudaStream_t stream);
+/* torch.complex(*tensor_split(xf,2,1)) + irfft2(s=(h,w)) (model/unidefense.py:142-145): xf [N,2C,h,w/2+1]
+ * (optionally multiplied on load by mask [N,h*(w/2+1)]) -> y [N,C,h,w].  adjoint_of_forward=1 gives
+ * rfft2's backward (fft_r2c_backward: zero-padded half spectrum, no mirroring).    */
+UD_API int ud_irfft2_cat(const float* xf, const float* mask, float* y, int N, int C, int h, int w, int norm_ortho,
+                         int adjoint_of_forward, cudaStream_t stream);
+/* out = (1-s)*smask*emb + s*ff + res, s = sigmoid(*fuse_coef) (model/unidefense.py:153-155).
+ * emb, ff, res, out [N,C,HW]; smask [N,HW]; res = dropout(emb.clone()) or NULL (= emb).             */
+UD_API int ud_attn_fuse_fwd(const float* emb, const float* smask, const float* ff, const float* res,
+                            const float* fuse_coef, float* out, int N, int C, int HW, cudaStream_t stream);
+UD_API size_t ud_attn_fuse_bwd_workspace_bytes(int N, int HW);
+UD_API int ud_attn_fuse_bwd(const float* emb, const float* smask, const float* ff, const float* g,
+                            const float* fuse_coef, float* g_emb, float* g_ff, float* g_smask, float* g_coef,
+                            void* ws, size_t ws_bytes, int N, int C, int HW, int res_is_emb, cudaStream_t stream);
+
+/* ---- a5 / a6: dynamic filters (model/modules.py:79-134) ---------------------------------------------
+ * Local BatchNorm statistics of x [N,C,HW]: mean[c], m2[c] = sum (x-mean)^2 over N*HW (the caller merges
+ * ranks for SyncBatchNorm, engine/forgery_engine.py:142, and derives rstd / running stats).          */
+UD_API int ud_bn_stats(const float* x, float* mean, float* m2, int N, int C, int HW, cudaStream_t stream);
+UD_API int ud_bn_bwd_reduce(const float* dz, const float* x, const float* mean, const float* rstd, float* sum_dz,
+                            float* sum_dz_xh, int N, int C, int HW, cudaStream_t stream);
+/* inv_count = 1/(global N*HW) in training, 0 in eval (running stats: pure scaling).                  */
+UD_API int ud_bn_bwd_apply(const float* dz, const float* x, const float* mean, const float* rstd,
+                           const float* gamma, const float* sum_dz, const float* sum_dz_xh, float inv_count,
+                           float* gx, int N, int C, int HW, cudaStream_t stream);
+/* Everything after layer1's conv: BN-apply + act + channel mean/max + cat(diff) + conv1x1 (w2 [2+D]) +
+ * sigmoid -> mask [N,HW]; out [N,Cx,HW] = mask*x (nullable).  proj [N,Cp,HW] is the raw conv output.
+ * pmean/pmax [N,HW] and argmax [N,HW] (first index on ties, like torch.max) are saved for backward.   */
+UD_API int ud_dyfi_mask_fwd(const float* proj, const float* bn_mean, const float* bn_rstd, const float* gamma,
+                            const float* beta, const float* diff, const float* w2, const float* x, float* mask,
+                            float* out, float* pmean, float* pmax, int* argmax, int N, int Cp, int D, int Cx, int HW,
+                            int act, cudaStream_t stream);
+UD_API size_t ud_dyfi_mask_bwd_workspace_bytes(int N, int HW);
+/* g_mask [N,HW] / g_out [N,Cx,HW] (either nullable) -> g_x = mask*g_out, dz [N,Cp,HW] (gradient w.r.t.
+ * the BN output, to be finished by ud_bn_bwd_*), g_w2 [2+D].                                          */
+UD_API int ud_dyfi_mask_bwd(const float* proj, const float* bn_mean, const float* bn_rstd, const float* gamma,
+                            const float* beta, const float* diff, const float* w2, const float* x, const float* mask,
+                            const float* pmean, const float* pmax, const int* argmax, const float* g_mask,
+                            const float* g_out, float* g_x, float* dz, float* g_w2, void* ws, size_t ws_bytes, int N,
+                            int Cp, int D, int Cx, int HW, int act, cudaStream_t stream);
+
+/* ---- a9-a11: losses; each also returns d loss / d input for upstream gradient 1 ------------------
+ * AsymmetricalWeightedTripletLoss.forward (loss/triplet_loss.py:75-82): feat [N,c], labels int64 [N]
+ * (label-0 rows are the anchors and come first), N <= 128.  gfeat nullable.                         */
+UD_API int ud_triplet_fwd(const float* feat, const long long* labels, float* loss, float* gfeat, int N, int c,
+                          cudaStream_t stream);
+/* FactorizationLoss.forward (loss/calib_loss.py:17-28): emb_a (grad), emb_b [N,F], 2 <= N <= 128.    */
+UD_API size_t ud_factorization_workspace_bytes(int N, int F);
+UD_API int ud_factorization_fwd(const float* emb_a, const float* emb_b, float* loss, float* g_a, void* ws,
+                                size_t ws_bytes, int N, int F, float off_diag_weight, float eps, cudaStream_t stream);
+/* KLDivLoss(batchmean, log_target)(log_softmax(pred.flat), log_softmax(gt.flat))
+ * (engine/abstract_engine.py:333-346): pred, gt [N,M].                                              */
+UD_API size_t ud_mask_kl_workspace_bytes(int N);
+UD_API int ud_mask_kl_fwd(const float* pred, const float* gt, float* loss, float* g_pred, void* ws, size_t ws_bytes,
+                          int N, int M, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

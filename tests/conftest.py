@@ -35,3 +35,14 @@ def golden_ops():
 def golden_path(request):
     import torch
     return torch.load(os.path.join(GOLDEN, f"path_{request.param}.pt"), weights_only=False)
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    """Parity is stated for fp32: keep the library convs/GEMMs around our kernels out of TF32."""
+    import torch
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

@@ -1,0 +1,130 @@
+"""a5/a6 parity: BN statistics + fused mask stage (fwd+bwd) vs the reference fixtures and the oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import recon_path as O
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, rtol=1e-4, atol=None):
+    b = b.detach()
+    scale = float(b.abs().max()) if b.numel() else 1.0
+    atol = (1e-5 * max(scale, 1e-6)) if atol is None else atol
+    torch.testing.assert_close(a.detach().cpu().to(b.dtype), b, rtol=rtol, atol=atol)
+
+
+def _run_cuda(x, diff, w1, gamma, beta, w2, act, training, rmean=None, rvar=None, want_out=True):
+    """DyFi forward with the conv in torch (library) and everything after it in our kernels."""
+    from unidefense_b200 import ops
+    proj = F.conv2d(x, w1, None, 1, w1.shape[-1] // 2)
+    N, C, h, w = proj.shape
+    if training:
+        mean, m2 = ops.bn_local_stats(proj.detach())
+        var = m2 / (N * h * w)
+        count = N * h * w
+    else:
+        mean, var, count = rmean, rvar, 0
+    rstd = torch.rsqrt(var + 1e-5)
+    mask, out = ops.dyfi_mask(proj, mean, rstd, gamma, beta, diff, w2, x, act, count, want_out)
+    return mask, out, mean, var
+
+
+def test_reference_fixture(golden_ops):
+    for c in golden_ops["dyfi"]:
+        sd = {k: v.cuda() for k, v in c["sd0"].items()}
+        x = c["x"].cuda().requires_grad_()
+        ps = [sd["layer1.0.weight"].clone().requires_grad_(), sd["layer1.1.weight"].clone().requires_grad_(),
+              sd["layer1.1.bias"].clone().requires_grad_(), sd["layer2.0.weight"].clone().requires_grad_()]
+        mask, out, mean, var = _run_cuda(x, c["diff"].cuda(), ps[0], ps[1], ps[2], ps[3], c["act"], True)
+        close(mask, c["mask"]); close(out, c["out"])
+        gs = torch.autograd.grad((mask * c["gm"].cuda()).sum() + (out * c["go"].cuda()).sum(), [x] + ps)
+        for a, k in zip(gs, ["gx", "gw1", "ggamma", "gbeta", "gw2"]):
+            close(a, c[k], rtol=2e-4, atol=2e-5 * float(c[k].abs().max()) + 1e-7)
+        n = c["x"].shape[0] * c["mask"].shape[-2] * c["mask"].shape[-1]
+        close(0.9 * sd["layer1.1.running_mean"] + 0.1 * mean, c["sd1"]["layer1.1.running_mean"])
+        close(0.9 * sd["layer1.1.running_var"] + 0.1 * var * n / (n - 1), c["sd1"]["layer1.1.running_var"])
+        sd1 = {k: v.cuda() for k, v in c["sd1"].items()}
+        with torch.no_grad():
+            me, oe, _, _ = _run_cuda(c["x"].cuda(), c["diff"].cuda(), sd1["layer1.0.weight"], sd1["layer1.1.weight"],
+                                     sd1["layer1.1.bias"], sd1["layer2.0.weight"], c["act"], False,
+                                     sd1["layer1.1.running_mean"], sd1["layer1.1.running_var"])
+        close(me, c["mask_eval"]); close(oe, c["out_eval"])
+
+
+# (kind, N, C, h, w): EB4 (544ch @12x7, 272 @12x12), R50 per-sample slice, R18, odd shapes
+CASES = [("freq", 4, 272, 12, 7), ("spat", 4, 272, 12, 12), ("freq", 2, 64, 8, 5), ("spat", 2, 48, 8, 8),
+         ("freq", 3, 5, 24, 13), ("spat", 3, 7, 24, 24), ("spat", 2, 9, 5, 7), ("freq", 1, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("act", ["swish", "relu"])
+@pytest.mark.parametrize("training", [True, False])
+def test_vs_oracle(case, act, training):
+    kind, N, C, h, w = case
+    if training and N * h * w < 2:
+        pytest.skip("batch statistics need more than one value per channel")
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    cin, D, k = (2 * C, 6, 1) if kind == "freq" else (C, 3, 3)
+    x = torch.randn(N, cin, h, w, generator=g)
+    diff = torch.rand(N, D, h, w, generator=g)
+    w1 = torch.randn(cin, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    gamma = torch.rand(cin, generator=g) + 0.5
+    beta = torch.randn(cin, generator=g) * 0.1
+    w2 = torch.randn(1, 2 + D, 1, 1, generator=g) * 0.5
+    rmean = torch.randn(cin, generator=g) * 0.2
+    rvar = torch.rand(cin, generator=g) + 0.5
+    gm = torch.randn(N, 1, h, w, generator=g)
+    go = torch.randn(N, cin, h, w, generator=g)
+    leaves = [x, w1, gamma, beta, w2]
+    tc = [t.cuda().requires_grad_() for t in leaves]
+    mask, out, _, _ = _run_cuda(tc[0], diff.cuda(), tc[1], tc[2], tc[3], tc[4], act, training, rmean.cuda(), rvar.cuda())
+    ((mask * gm.cuda()).sum() + (out * go.cuda()).sum()).backward()
+    t64 = [t.double().requires_grad_() for t in leaves]
+    m64, o64, _ = O.dynamic_filter(t64[0], diff.double(), t64[1], t64[2], t64[3], t64[4], act, training,
+                                   rmean.double(), rvar.double())
+    ((m64 * gm.double()).sum() + (o64 * go.double()).sum()).backward()
+    close(mask, m64); close(out, o64)
+    for a, b in zip(tc, t64):
+        close(a.grad, b.grad, rtol=3e-4, atol=3e-5 * float(b.grad.abs().max()) + 1e-7)
+
+
+def test_mask_only_path():
+    """The spatial filter's product mask*emb is folded into the fuse kernel: want_out=False."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 6, 5, 5, generator=g)
+    diff = torch.rand(2, 3, 5, 5, generator=g)
+    w1 = torch.randn(6, 6, 3, 3, generator=g) * 0.2
+    gamma, beta = torch.rand(6, generator=g) + 0.5, torch.randn(6, generator=g) * 0.1
+    w2 = torch.randn(1, 5, 1, 1, generator=g)
+    gm = torch.randn(2, 1, 5, 5, generator=g)
+    leaves = [x, w1, gamma, beta, w2]
+    tc = [t.cuda().requires_grad_() for t in leaves]
+    mask, out, _, _ = _run_cuda(tc[0], diff.cuda(), tc[1], tc[2], tc[3], tc[4], "swish", True, want_out=False)
+    assert out is None
+    (mask * gm.cuda()).sum().backward()
+    t64 = [t.double().requires_grad_() for t in leaves]
+    m64, _, _ = O.dynamic_filter(t64[0], diff.double(), t64[1], t64[2], t64[3], t64[4], "swish", True)
+    (m64 * gm.double()).sum().backward()
+    close(mask, m64)
+    for a, b in zip(tc, t64):
+        close(a.grad, b.grad, rtol=3e-4, atol=3e-5 * float(b.grad.abs().max()) + 1e-7)
+
+
+def test_argmax_ties_first_index():
+    """relu makes exact ties (0) common: torch.max takes the first index; gradient must follow it."""
+    from unidefense_b200 import ops
+    N, C, h, w = 1, 4, 2, 2
+    proj = -torch.ones(N, C, h, w, device="cuda")           # every channel -> relu 0: all tie
+    proj[0, 2, 0, 0] = 3.0
+    mean = torch.zeros(C, device="cuda"); rstd = torch.ones(C, device="cuda")
+    diff = torch.zeros(N, 3, h, w, device="cuda")
+    w2 = torch.tensor([0.0, 1.0, 0, 0, 0], device="cuda").view(1, 5, 1, 1)
+    x = torch.ones(N, C, h, w, device="cuda")
+    p = proj.clone().requires_grad_()
+    mask, _ = ops.dyfi_mask(p, mean, rstd, None, None, diff, w2, x, "relu", 0, False)
+    mask.sum().backward()
+    g = p.grad
+    assert float(g[0, 2, 0, 0]) > 0      # the unique max gets the gradient
+    assert float(g[0, :, 0, 1].abs().sum()) == 0   # ties at relu(−1)=0 -> act' = 0 anyway

@@ -39,11 +39,13 @@ def test_forward_vs_oracle(shape, norm):
     dec, x = _inputs(shape)
     rec, sp, fr = ops.recon_tail(dec.cuda(), x.cuda(), norm)
     rec64, sp64, fr64 = O.recon_tail(dec.double(), x.double(), norm)
-    torch.testing.assert_close(rec.cpu().double(), rec64, rtol=1e-5, atol=1e-6)
+    # (the fp64 oracle also evaluates the resize coordinates in fp64; ATen and the kernel use fp32)
+    torch.testing.assert_close(rec.cpu().double(), rec64, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(sp.cpu().double(), sp64, rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(fr.cpu().double(), fr64, rtol=1e-4, atol=1e-7)
     # and against the fp32 two-FFT formulation the reference actually runs
-    _, sp32, fr32 = O.recon_tail(dec, x, norm)
+    rec32, sp32, fr32 = O.recon_tail(dec, x, norm)
+    torch.testing.assert_close(rec.cpu(), rec32, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(sp.cpu(), sp32, rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(fr.cpu(), fr32, rtol=1e-4, atol=1e-7)
 

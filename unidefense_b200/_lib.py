@@ -28,6 +28,30 @@ SIGNATURES = {
     "ud_recon_tail_signs_bytes": (c_sz, [c_i] * 4),
     "ud_recon_tail_fwd": (c_i, [c_p] * 7 + [c_sz] + [c_i] * 7 + [c_p]),
     "ud_recon_tail_bwd": (c_i, [c_p] * 7 + [c_sz] + [c_i] * 7 + [c_p]),
+    "ud_in_act_fwd": (c_i, [c_p] * 7 + [c_i] * 3 + [c_f, c_i, c_p]),
+    "ud_in_act_bwd_workspace_bytes": (c_sz, [c_i, c_i]),
+    "ud_in_act_bwd": (c_i, [c_p] * 11 + [c_sz] + [c_i] * 4 + [c_p]),
+    "ud_tanh_fwd": (c_i, [c_p, c_p, ctypes.c_longlong, c_p]),
+    "ud_tanh_bwd": (c_i, [c_p, c_p, c_p, ctypes.c_longlong, c_p]),
+    "ud_bilinear_ac_fwd": (c_i, [c_p, c_p] + [c_i] * 5 + [c_p]),
+    "ud_bilinear_ac_bwd": (c_i, [c_p, c_p] + [c_i] * 5 + [c_p]),
+    "ud_attn_prep": (c_i, [c_p] * 4 + [c_i] * 9 + [c_p]),
+    "ud_rfft2_cat": (c_i, [c_p, c_p] + [c_i] * 6 + [c_p]),
+    "ud_irfft2_cat": (c_i, [c_p, c_p, c_p] + [c_i] * 6 + [c_p]),
+    "ud_attn_fuse_fwd": (c_i, [c_p] * 6 + [c_i] * 3 + [c_p]),
+    "ud_attn_fuse_bwd_workspace_bytes": (c_sz, [c_i, c_i]),
+    "ud_attn_fuse_bwd": (c_i, [c_p] * 10 + [c_sz] + [c_i] * 4 + [c_p]),
+    "ud_bn_stats": (c_i, [c_p] * 3 + [c_i] * 3 + [c_p]),
+    "ud_bn_bwd_reduce": (c_i, [c_p] * 6 + [c_i] * 3 + [c_p]),
+    "ud_bn_bwd_apply": (c_i, [c_p] * 7 + [c_f, c_p] + [c_i] * 3 + [c_p]),
+    "ud_dyfi_mask_fwd": (c_i, [c_p] * 13 + [c_i] * 6 + [c_p]),
+    "ud_dyfi_mask_bwd_workspace_bytes": (c_sz, [c_i, c_i]),
+    "ud_dyfi_mask_bwd": (c_i, [c_p] * 18 + [c_sz] + [c_i] * 6 + [c_p]),
+    "ud_triplet_fwd": (c_i, [c_p] * 4 + [c_i, c_i, c_p]),
+    "ud_factorization_workspace_bytes": (c_sz, [c_i, c_i]),
+    "ud_factorization_fwd": (c_i, [c_p] * 5 + [c_sz, c_i, c_i, c_f, c_f, c_p]),
+    "ud_mask_kl_workspace_bytes": (c_sz, [c_i]),
+    "ud_mask_kl_fwd": (c_i, [c_p] * 5 + [c_sz, c_i, c_i, c_p]),
 }
 
 

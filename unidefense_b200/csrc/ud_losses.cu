@@ -1,0 +1,403 @@
+// a9 / a10 / a11 -- losses, each fused forward + gradient, no host syncs     
+//
+//  a9  AsymmetricalWeightedTripletLoss   loss/triplet_loss.py:16-82
+//  a10 FactorizationLoss                 loss/calib_loss.py:17-28
+//  a11 mask KL alignment                 engine/abstract_engine.py:331-346 (KLDivLoss batchmean, log_target)
+//
+// Every kernel here also emits d loss / d input for upstream gradient 1, so autograd's backward is
+// a scalar multiply; the reference's boolean-mask indexing / torch.where host sync
+// (triplet_loss.py:39,51,53) disappears.  All reductions are fixed-order (deterministic).
+#include "../../include/unidefense_b200.h"
+#include "ud_common.cuh"
+
+#define LS_MAX_N 128
+
+// ---------------------------------------------------------------- a9 triplet
+// one CTA; dynamic smem: dist [nr][N], H [nr][N], sq [N], gu [nr], fp [nr], fn [nr]
+__global__ void __launch_bounds__(256)
+ls_triplet_kernel(const float* __restrict__ feat, const long long* __restrict__ labels, float* __restrict__ loss,
+                  float* __restrict__ gfeat, int N, int c) {
+  extern __shared__ float smf[];
+  __shared__ int s_nr;
+  __shared__ float red[33];
+  __shared__ int s_lab[LS_MAX_N];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  if (tid == 0) s_nr = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += nth) {
+    const int l = (int)labels[i];
+    s_lab[i] = l;
+    if (l == 0) atomicAdd(&s_nr, 1);  // N_real = #(labels == 0)   (triplet_loss.py:39)
+  }
+  __syncthreads();
+  const int nr = s_nr;
+  float* dist = smf;
+  float* Hm = dist + N * N;
+  float* sq = Hm + N * N;
+  float* gu = sq + N;
+  float* fpv = gu + N;
+  float* fnv = fpv + N;
+  // squared norms
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nth >> 5;
+  for (int i = warp; i < N; i += nwarps) {
+    float s = 0.f;
+    for (int k = lane; k < c; k += 32) {
+      const float v = feat[(long long)i * c + k];
+      s = fmaf(v, v, s);
+    }
+    s = ud_warp_sum(s);
+    if (lane == 0) sq[i] = s;
+  }
+  __syncthreads();
+  // distances for anchor rows: one warp per (i, j) pair
+  for (int p = warp; p < nr * N; p += nwarps) {
+    const int i = p / N, j = p - i * N;
+    float s = 0.f;
+    for (int k = lane; k < c; k += 32) s = fmaf(feat[(long long)i * c + k], feat[(long long)j * c + k], s);
+    s = ud_warp_sum(s);
+    if (lane == 0) {
+      const float q = sq[i] + sq[j] - 2.f * s;
+      dist[i * N + j] = sqrtf(fmaxf(q, 1e-12f));
+      Hm[i * N + j] = (q >= 1e-12f) ? 1.f : 0.f;  // clamp(min) passes gradient only where q >= min
+    }
+  }
+  __syncthreads();
+  // per-anchor weighted sums: one warp per anchor
+  const float eps = 1e-12f;
+  float lsum = 0.f;
+  for (int i = warp; i < nr; i += nwarps) {
+    const int li = s_lab[i];
+    float sp = 0.f, sn = 0.f, dp = 0.f, dn = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      const float d = dist[i * N + j];
+      if (s_lab[j] == li) {
+        if (j != i) {
+          const float e = expf(d);
+          sp += e;
+          dp = fmaf(e, d, dp);
+        }
+      } else {
+        const float e = expf(-d);
+        sn += e;
+        dn = fmaf(e, d, dn);
+      }
+    }
+    sp = ud_warp_sum(sp); sn = ud_warp_sum(sn); dp = ud_warp_sum(dp); dn = ud_warp_sum(dn);
+    const float fp = dp / (sp + eps), fn = dn / (sn + eps);
+    const float u = fn - fp;
+    // SoftMarginLoss(u, 1) = log(1 + exp(-u)); d/du = -sigmoid(-u)
+    const float l = (u > 0.f) ? log1pf(expf(-u)) : (-u + log1pf(expf(u)));
+    if (lane == 0) {
+      lsum += l;
+      fpv[i] = fp;
+      fnv[i] = fn;
+      gu[i] = -1.f / (1.f + expf(u)) / (float)nr;
+    }
+    // dL/dd_ij -> H_ij = (dL/dd_ij) / d_ij (masked by the clamp)
+    for (int j = lane; j < N; j += 32) {
+      const float d = dist[i * N + j];
+      float g = 0.f;
+      const float gui = -1.f / (1.f + expf(u)) / (float)nr;
+      if (s_lab[j] == li) {
+        if (j != i) g = -gui * (expf(d) / (sp + eps)) * (1.f + d - fp);
+      } else {
+        g = gui * (expf(-d) / (sn + eps)) * (1.f - d + fn);
+      }
+      Hm[i * N + j] = Hm[i * N + j] * g / d;
+    }
+  }
+  lsum = ud_block_sum(lsum, red);  // also orders the Hm writes before the reads below
+  if (tid == 0) *loss = (nr > 0) ? lsum / (float)nr : 0.f;
+  if (gfeat == nullptr) return;
+  // gx_m = x_m * rowsum(Hs)_m - sum_j Hs_mj x_j,  Hs = H + H^T (rows >= nr of H are zero)
+  for (int m = warp; m < N; m += nwarps) {
+    float rs = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      float h = 0.f;
+      if (m < nr) h += Hm[m * N + j];
+      if (j < nr) h += Hm[j * N + m];
+      rs += h;
+    }
+    rs = ud_warp_sum(rs);
+    for (int k = lane; k < c; k += 32) {
+      float acc = feat[(long long)m * c + k] * rs;
+      for (int j = 0; j < N; ++j) {
+        float h = 0.f;
+        if (m < nr) h += Hm[m * N + j];
+        if (j < nr) h += Hm[j * N + m];
+        acc = fmaf(-h, feat[(long long)j * c + k], acc);
+      }
+      gfeat[(long long)m * c + k] = acc;
+    }
+  }
+}
+
+extern "C" int ud_triplet_fwd(const float* feat, const long long* labels, float* loss, float* gfeat, int N, int c,
+                              cudaStream_t stream) {
+  UD_REQUIRE(N >= 1 && c >= 1, UD_ERR_INVALID, "triplet: bad shape N=%d c=%d", N, c);
+  UD_REQUIRE(N <= LS_MAX_N, UD_ERR_UNSUPPORTED, "triplet: per-rank batch %d > %d unsupported", N, LS_MAX_N);
+  UD_REQUIRE(feat && labels && loss, UD_ERR_INVALID, "triplet: null pointer");
+  const size_t smem = sizeof(float) * (2ull * N * N + 4ull * N);
+  if (smem > (48u << 10))
+    UD_CUDA(cudaFuncSetAttribute(ls_triplet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ls_triplet_kernel<<<1, 256, smem, stream>>>(feat, labels, loss, gfeat, N, c);
+  return ud_check_launch("triplet");
+}
+
+// ---------------------------------------------------------------- a10 factorization
+#define FC_CHUNK 64   // features per CTA
+
+// per-feature statistics, normalised copies, diagonal of c, partial Grams.   grid = ceil(F/FC_CHUNK), block 256
+__global__ void __launch_bounds__(256)
+ls_fac_stats_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ ah,
+                    float* __restrict__ bh, float* __restrict__ ra, float* __restrict__ sa, float* __restrict__ cdiag,
+                    float* __restrict__ part_on, float* __restrict__ part_dd, float* __restrict__ gram_part, int N,
+                    int F, float eps) {
+  extern __shared__ float smf[];
+  __shared__ float red[33];
+  float* tA = smf;                 // [N][FC_CHUNK]
+  float* tB = tA + N * FC_CHUNK;   // [N][FC_CHUNK]
+  const int f0 = blockIdx.x * FC_CHUNK;
+  const int tid = threadIdx.x;
+  float on = 0.f, dd = 0.f;
+  if (tid < FC_CHUNK) {
+    const int f = f0 + tid;
+    if (f < F) {
+      float ma = 0.f, mb = 0.f;
+      for (int n = 0; n < N; ++n) {
+        ma += a[(long long)n * F + f];
+        mb += b[(long long)n * F + f];
+      }
+      ma /= (float)N;
+      mb /= (float)N;
+      float va = 0.f, vb = 0.f;
+      for (int n = 0; n < N; ++n) {
+        const float da = a[(long long)n * F + f] - ma, db = b[(long long)n * F + f] - mb;
+        va = fmaf(da, da, va);
+        vb = fmaf(db, db, vb);
+      }
+      const float stda = sqrtf(va / (float)(N - 1)), stdb = sqrtf(vb / (float)(N - 1));   // unbiased (calib_loss.py:20-21)
+      const float r_a = 1.f / (stda + eps), r_b = 1.f / (stdb + eps);
+      float cd = 0.f;
+      for (int n = 0; n < N; ++n) {
+        const float xa = (a[(long long)n * F + f] - ma) * r_a, xb = (b[(long long)n * F + f] - mb) * r_b;
+        tA[n * FC_CHUNK + tid] = xa;
+        tB[n * FC_CHUNK + tid] = xb;
+        ah[(long long)n * F + f] = xa;
+        bh[(long long)n * F + f] = xb;
+        cd = fmaf(xa, xb, cd);
+      }
+      cd /= (float)N;
+      ra[f] = r_a;
+      sa[f] = stda;
+      cdiag[f] = cd;
+      on = (cd - 1.f) * (cd - 1.f);
+      dd = cd * cd;
+    } else {
+      for (int n = 0; n < N; ++n) {
+        tA[n * FC_CHUNK + tid] = 0.f;
+        tB[n * FC_CHUNK + tid] = 0.f;
+      }
+    }
+  }
+  on = ud_block_sum(on, red);
+  dd = ud_block_sum(dd, red);
+  if (tid == 0) {
+    part_on[blockIdx.x] = on;
+    part_dd[blockIdx.x] = dd;
+  }
+  // partial Grams over this chunk: GA[m][n] = sum_f Ah[m,f] Ah[n,f], GB likewise
+  float* gp = gram_part + (long long)blockIdx.x * 2 * N * N;
+  for (int p = tid; p < N * N; p += blockDim.x) {
+    const int m = p / N, n = p - m * N;
+    float ga = 0.f, gb = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < FC_CHUNK; ++k) {
+      ga = fmaf(tA[m * FC_CHUNK + k], tA[n * FC_CHUNK + k], ga);
+      gb = fmaf(tB[m * FC_CHUNK + k], tB[n * FC_CHUNK + k], gb);
+    }
+    gp[p] = ga;
+    gp[N * N + p] = gb;
+  }
+}
+
+// single CTA: sum the partials in fixed order, loss, and GB for the backward
+__global__ void __launch_bounds__(256)
+ls_fac_loss_kernel(const float* __restrict__ part_on, const float* __restrict__ part_dd,
+                   const float* __restrict__ gram_part, float* __restrict__ GB, float* __restrict__ loss, int N, int F,
+                   int nchunks, float off_w) {
+  __shared__ float red[33];
+  float dot = 0.f;
+  for (int p = threadIdx.x; p < N * N; p += blockDim.x) {
+    float ga = 0.f, gb = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      ga += gram_part[(long long)ch * 2 * N * N + p];
+      gb += gram_part[(long long)ch * 2 * N * N + N * N + p];
+    }
+    GB[p] = gb;
+    dot = fmaf(ga, gb, dot);
+  }
+  dot = ud_block_sum(dot, red);
+  float on = 0.f, dd = 0.f;
+  for (int i = threadIdx.x; i < nchunks; i += blockDim.x) {
+    on += part_on[i];
+    dd += part_dd[i];
+  }
+  on = ud_block_sum(on, red);
+  dd = ud_block_sum(dd, red);
+  if (threadIdx.x == 0) {
+    const float sumsq = dot / ((float)N * (float)N);      // sum_ij c_ij^2 = <Ah Ah^T, Bh Bh^T> / N^2
+    const float off = (F > 1) ? (sumsq - dd) / ((float)F * (float)(F - 1)) : 0.f;
+    *loss = on / (float)F + off_w * off;
+  }
+}
+
+// d loss / d emb_a (upstream 1).   grid = ceil(F/FC_CHUNK), block 256 (thread = (n-group, feature))
+__global__ void __launch_bounds__(256)
+ls_fac_grad_kernel(const float* __restrict__ a, const float* __restrict__ ah, const float* __restrict__ bh,
+                   const float* __restrict__ ra, const float* __restrict__ sa, const float* __restrict__ cdiag,
+                   const float* __restrict__ GB, float* __restrict__ ga, int N, int F, float off_w) {
+  extern __shared__ float smf[];
+  float* dA = smf;  // [N][FC_CHUNK]
+  const int f0 = blockIdx.x * FC_CHUNK;
+  const int fl = threadIdx.x % FC_CHUNK, ng = threadIdx.x / FC_CHUNK, ngs = blockDim.x / FC_CHUNK;
+  const int f = f0 + fl;
+  const float k_off = (F > 1) ? 2.f * off_w / ((float)F * (float)(F - 1)) : 0.f;
+  const float k_on = 2.f / (float)F;
+  const float invN = 1.f / (float)N;
+  if (f < F) {
+    const float cd = cdiag[f];
+    for (int n = ng; n < N; n += ngs) {
+      float t = 0.f;  // (GB Ah)[n, f]
+      for (int m = 0; m < N; ++m) t = fmaf(GB[n * N + m], ah[(long long)m * F + f], t);
+      const float bv = bh[(long long)n * F + f];
+      dA[n * FC_CHUNK + fl] = invN * (k_off * (invN * t - cd * bv) + k_on * (cd - 1.f) * bv);
+    }
+  }
+  __syncthreads();
+  if (f < F && ng == 0) {
+    // through Ah = (a - mean) * r, r = 1/(std + eps), std unbiased
+    float m1 = 0.f, m2 = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float d = dA[n * FC_CHUNK + fl];
+      m1 += d;
+      m2 = fmaf(d, ah[(long long)n * F + f], m2);  // sum dA * t * r
+    }
+    m1 *= invN;
+    const float r = ra[f], s = sa[f];
+    // dL/da_n = r (dA_n - mean dA) - r^2 (sum_m dA_m t_m) t_n / ((N-1) s),  t = Ah / r
+    const float k2 = (s > 0.f) ? (m2 / r) * r * r / ((float)(N - 1) * s) : 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float t_n = ah[(long long)n * F + f] / r;
+      ga[(long long)n * F + f] = r * (dA[n * FC_CHUNK + fl] - m1) - k2 * t_n;
+    }
+  }
+}
+
+extern "C" size_t ud_factorization_workspace_bytes(int N, int F) {
+  const size_t nch = ud_cdiv(F, FC_CHUNK);
+  return sizeof(float) * (2ull * N * F + 3ull * F + 2ull * nch + nch * 2ull * N * N + (size_t)N * N) + 256;
+}
+
+extern "C" int ud_factorization_fwd(const float* emb_a, const float* emb_b, float* loss, float* g_a, void* ws,
+                                    size_t ws_bytes, int N, int F, float off_diag_weight, float eps,
+                                    cudaStream_t stream) {
+  UD_REQUIRE(N >= 2 && F >= 1, UD_ERR_INVALID, "factorization: needs N >= 2 (unbiased std), got N=%d F=%d", N, F);
+  UD_REQUIRE(N <= LS_MAX_N, UD_ERR_UNSUPPORTED, "factorization: per-rank batch %d > %d unsupported", N, LS_MAX_N);
+  UD_REQUIRE(emb_a && emb_b && loss && ws, UD_ERR_INVALID, "factorization: null pointer");
+  UD_REQUIRE(ws_bytes >= ud_factorization_workspace_bytes(N, F), UD_ERR_WORKSPACE, "factorization: workspace too small");
+  const int nch = ud_cdiv(F, FC_CHUNK);
+  float* p = static_cast<float*>(ws);
+  float* ah = p; p += (size_t)N * F;
+  float* bh = p; p += (size_t)N * F;
+  float* ra = p; p += F;
+  float* sa = p; p += F;
+  float* cdiag = p; p += F;
+  float* part_on = p; p += nch;
+  float* part_dd = p; p += nch;
+  float* gram_part = p; p += (size_t)nch * 2 * N * N;
+  float* GB = p;
+  const size_t smem = sizeof(float) * 2ull * N * FC_CHUNK;
+  if (smem > (48u << 10)) {
+    UD_CUDA(cudaFuncSetAttribute(ls_fac_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  ls_fac_stats_kernel<<<nch, 256, smem, stream>>>(emb_a, emb_b, ah, bh, ra, sa, cdiag, part_on, part_dd, gram_part, N,
+                                                  F, eps);
+  int rc = ud_check_launch("fac_stats");
+  if (rc != UD_OK) return rc;
+  ls_fac_loss_kernel<<<1, 256, 0, stream>>>(part_on, part_dd, gram_part, GB, loss, N, F, nch, off_diag_weight);
+  if ((rc = ud_check_launch("fac_loss")) != UD_OK) return rc;
+  if (g_a != nullptr) {
+    ls_fac_grad_kernel<<<nch, 256, sizeof(float) * (size_t)N * FC_CHUNK, stream>>>(emb_a, ah, bh, ra, sa, cdiag, GB,
+                                                                                   g_a, N, F, off_diag_weight);
+    rc = ud_check_launch("fac_grad");
+  }
+  return rc;
+}
+
+// ---------------------------------------------------------------- a11 mask KL
+// loss = sum_n sum_m softmax(gt)_m (log_softmax(gt)_m - log_softmax(pred)_m) / N ; g_pred = (softmax(pred) - softmax(gt))/N
+__global__ void __launch_bounds__(128)
+ls_mask_kl_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* __restrict__ row_loss,
+                  float* __restrict__ g_pred, int N, int M) {
+  __shared__ float red[33];
+  const int n = blockIdx.x;
+  const float* p = pred + (long long)n * M;
+  const float* q = gt + (long long)n * M;
+  float mp = -INFINITY, mq = -INFINITY;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    mp = fmaxf(mp, p[i]);
+    mq = fmaxf(mq, q[i]);
+  }
+  // block max via the sum helper on a warp-max: do a two-step reduce
+  mp = ud_warp_max(mp);
+  mq = ud_warp_max(mq);
+  __shared__ float smax[2][4];
+  if ((threadIdx.x & 31) == 0) {
+    smax[0][threadIdx.x >> 5] = mp;
+    smax[1][threadIdx.x >> 5] = mq;
+  }
+  __syncthreads();
+  mp = fmaxf(fmaxf(smax[0][0], smax[0][1]), fmaxf(smax[0][2], smax[0][3]));
+  mq = fmaxf(fmaxf(smax[1][0], smax[1][1]), fmaxf(smax[1][2], smax[1][3]));
+  float sp = 0.f, sq = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    sp += expf(p[i] - mp);
+    sq += expf(q[i] - mq);
+  }
+  sp = ud_block_sum(sp, red);
+  sq = ud_block_sum(sq, red);
+  const float lzp = mp + logf(sp), lzq = mq + logf(sq);
+  float l = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const float lp = p[i] - lzp, lq = q[i] - lzq;
+    const float eq = expf(lq);
+    l = fmaf(eq, lq - lp, l);
+    if (g_pred) g_pred[(long long)n * M + i] = (expf(lp) - eq) / (float)N;
+  }
+  l = ud_block_sum(l, red);
+  if (threadIdx.x == 0) row_loss[n] = l / (float)N;
+}
+
+__global__ void ls_sum_kernel(const float* __restrict__ v, float* __restrict__ out, int n) {
+  __shared__ float red[33];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += v[i];
+  a = ud_block_sum(a, red);
+  if (threadIdx.x == 0) *out = a;
+}
+
+extern "C" size_t ud_mask_kl_workspace_bytes(int N) { return sizeof(float) * (size_t)(N > 0 ? N : 1); }
+
+extern "C" int ud_mask_kl_fwd(const float* pred, const float* gt, float* loss, float* g_pred, void* ws, size_t ws_bytes,
+                              int N, int M, cudaStream_t stream) {
+  UD_REQUIRE(N >= 1 && M >= 1, UD_ERR_INVALID, "mask_kl: bad shape N=%d M=%d", N, M);
+  UD_REQUIRE(pred && gt && loss && ws, UD_ERR_INVALID, "mask_kl: null pointer");
+  UD_REQUIRE(ws_bytes >= ud_mask_kl_workspace_bytes(N), UD_ERR_WORKSPACE, "mask_kl: workspace too small");
+  float* rows = static_cast<float*>(ws);
+  ls_mask_kl_kernel<<<N, 128, 0, stream>>>(pred, gt, rows, g_pred, N, M);
+  int rc = ud_check_launch("mask_kl");
+  if (rc != UD_OK) return rc;
+  ls_sum_kernel<<<1, 128, 0, stream>>>(rows, loss, N);
+  return ud_check_launch("mask_kl_sum");
+}

@@ -1,0 +1,86 @@
+"""Spatial-frequency convolutions of the backbones (stock torch; SURVEY.md §8a row a17, scope "next").
+
+Reference: SFConv2dStaticSamePadding (model/efficientnet/exp.py:7-65) and SFConv2d
+(model/resnet/exp.py:21-54).  Both are an nn.Conv2d (the spatial branch, so the pretrained
+`weight` key loads unchanged) that owns a second dense 1x1 convolution `freq_conv` on the
+cat([re, im]) half spectrum and a scalar gate `sf_coef` (init -10):
+
+    y = (1 - sigmoid(sf_coef)) * conv(x) + sigmoid(sf_coef) * pool(irfft2(freq_conv(cat rfft2(x))))
+
+The north star keeps the backbone on stock torch, so this file is plain PyTorch; the FFTs are
+computed in fp32 even under bf16 autocast (torch.complex rejects bf16).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _freq_branch(x, freq_conv, out_hw, norm):
+    size = x.shape[-2:]
+    with torch.autocast(device_type=x.device.type, enabled=False):
+        spec = torch.fft.rfft2(x.float(), norm=norm)
+        planar = torch.cat([spec.real, spec.imag], dim=1)
+    planar = freq_conv(planar)
+    with torch.autocast(device_type=x.device.type, enabled=False):
+        re, im = torch.tensor_split(planar.float(), 2, dim=1)
+        y = torch.fft.irfft2(torch.complex(re, im), s=size, norm=norm)
+    if tuple(y.shape[-2:]) != tuple(out_hw):
+        y = F.adaptive_avg_pool2d(y, out_hw)
+    return y
+
+
+class SFConv2d(nn.Conv2d):
+    """model/resnet/exp.py:21-54."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, freq_norm=None, **kwargs):
+        super().__init__(in_channels, out_channels, kernel_size, stride, **kwargs)
+        self.freq_norm = freq_norm
+        self.freq_conv = nn.Conv2d(in_channels * 2, out_channels * 2, kernel_size=1, bias=False)
+        self.sf_coef = nn.Parameter(torch.tensor(-10.0))
+
+    def forward(self, x):
+        spat = self._conv_forward(x, self.weight, self.bias)
+        freq = _freq_branch(x, self.freq_conv, spat.shape[-2:], self.freq_norm)
+        gate = torch.sigmoid(self.sf_coef)
+        return (1.0 - gate) * spat + gate * freq
+
+
+def same_pad_amounts(size, kernel, stride, dilation=1):
+    """TensorFlow 'SAME' padding for a nominal input extent -> (before, after)."""
+    out = math.ceil(size / stride)
+    total = max((out - 1) * stride + (kernel - 1) * dilation + 1 - size, 0)
+    return total // 2, total - total // 2
+
+
+class SamePadConv2d(nn.Conv2d):
+    """Conv2d with static TF-'SAME' padding computed from the nominal image size at construction
+    (model/efficientnet/utils.py Conv2dStaticSamePadding); keeps a parameter-free `static_padding`
+    child like the reference so module trees line up."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, image_size=None, **kwargs):
+        super().__init__(in_channels, out_channels, kernel_size, stride, **kwargs)
+        ih, iw = (image_size, image_size) if isinstance(image_size, int) else image_size
+        top, bottom = same_pad_amounts(ih, self.kernel_size[0], self.stride[0], self.dilation[0])
+        left, right = same_pad_amounts(iw, self.kernel_size[1], self.stride[1], self.dilation[1])
+        self.static_padding = nn.ZeroPad2d((left, right, top, bottom)) if (top + bottom + left + right) else nn.Identity()
+
+    def forward(self, x):
+        return self._conv_forward(self.static_padding(x), self.weight, self.bias)
+
+
+class SFSamePadConv2d(SamePadConv2d):
+    """model/efficientnet/exp.py:7-65."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, image_size=None, freq_norm=None, **kwargs):
+        super().__init__(in_channels, out_channels, kernel_size, stride, image_size=image_size, **kwargs)
+        self.freq_norm = freq_norm
+        self.freq_conv = nn.Conv2d(in_channels * 2, out_channels * 2, kernel_size=1, bias=False)
+        self.sf_coef = nn.Parameter(torch.tensor(-10.0))
+
+    def forward(self, x):
+        spat = self._conv_forward(self.static_padding(x), self.weight, self.bias)
+        freq = _freq_branch(x, self.freq_conv, spat.shape[-2:], self.freq_norm)
+        gate = torch.sigmoid(self.sf_coef)
+        return (1.0 - gate) * spat + gate * freq

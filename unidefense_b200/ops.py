@@ -55,3 +55,396 @@ def recon_tail(dec, x, norm="ortho"):
     """-> (rec [N,C,H,W], spatial [N], freq [N]); `rec` carries no grad (it is only returned for
     visualisation/eval by the reference, engine/forgery_engine.py:343-347)."""
     return _ReconTail.apply(dec, x, norm == "ortho")
+
+
+ACT_CODES = {"none": 0, "relu": 1, "swish": 2}
+
+
+class _InAct(torch.autograd.Function):
+    """a2: InstanceNorm2d(affine) + Swish/ReLU in one pass (model/unidefense.py:61-98 etc.)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, act, eps, want_mean):
+        x = x.contiguous()
+        L.require_cuda_f32(x, gamma, beta)
+        N, C = x.shape[:2]
+        HW = x[0, 0].numel() if N > 0 else int(torch.tensor(x.shape[2:]).prod())
+        lib = L.lib()
+        y = torch.empty_like(x)
+        mean = torch.empty(N * C, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(N * C, device=x.device, dtype=torch.float32)
+        ymean = torch.empty(N, C, device=x.device, dtype=torch.float32) if want_mean else None
+        L.check(lib.ud_in_act_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ptr(mean), L.ptr(rstd),
+                                  L.ptr(ymean), N, C, HW, float(eps), act, L.stream()), "in_act_fwd")
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        ctx.act = act
+        ctx.hw = HW
+        if want_mean:
+            return y, ymean
+        return y, None
+
+    @staticmethod
+    def backward(ctx, gy, g_ymean):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        N, C = x.shape[:2]
+        lib = L.lib()
+        gy = torch.zeros_like(x) if gy is None else gy.contiguous()
+        if g_ymean is not None:
+            g_ymean = g_ymean.contiguous()
+        gx = torch.empty_like(x)
+        ggamma = torch.empty_like(gamma) if gamma is not None else None
+        gbeta = torch.empty_like(beta) if beta is not None else None
+        nws = lib.ud_in_act_bwd_workspace_bytes(N, C)
+        ws = L.workspace(nws, x.device)
+        L.check(lib.ud_in_act_bwd(L.ptr(x), L.ptr(gy), L.ptr(gamma), L.ptr(beta), L.ptr(mean), L.ptr(rstd),
+                                  L.ptr(g_ymean), L.ptr(gx), L.ptr(ggamma), L.ptr(gbeta), L.ptr(ws), ws.numel(),
+                                  N, C, ctx.hw, ctx.act, L.stream()), "in_act_bwd")
+        return gx, ggamma, gbeta, None, None, None
+
+
+def in_act(x, gamma, beta, act="swish", eps=1e-5, want_mean=False):
+    """y = act(instance_norm(x)*gamma+beta); with want_mean also returns y.mean([-2,-1]) [N,C]."""
+    y, ymean = _InAct.apply(x, gamma, beta, ACT_CODES[act], eps, want_mean)
+    return (y, ymean) if want_mean else y
+
+
+class _Tanh(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        L.require_cuda_f32(x)
+        y = torch.empty_like(x)
+        L.check(L.lib().ud_tanh_fwd(L.ptr(x), L.ptr(y), x.numel(), L.stream()), "tanh_fwd")
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = torch.empty_like(y)
+        L.check(L.lib().ud_tanh_bwd(L.ptr(y), L.ptr(gy), L.ptr(gx), y.numel(), L.stream()), "tanh_bwd")
+        return gx
+
+
+def tanh(x):
+    return _Tanh.apply(x)
+
+
+# ------------------------------------------------------------------------------------------
+# a4 / a7: attention() glue
+# ------------------------------------------------------------------------------------------
+class _BilinearAC(torch.autograd.Function):
+    """F.interpolate(mode='bilinear', align_corners=True) (model/unidefense.py:16)."""
+
+    @staticmethod
+    def forward(ctx, x, H, W):
+        x = x.contiguous()
+        L.require_cuda_f32(x)
+        h, w = x.shape[-2:]
+        planes = x.numel() // (h * w) if h * w else 0
+        y = torch.empty(*x.shape[:-2], H, W, device=x.device, dtype=torch.float32)
+        L.check(L.lib().ud_bilinear_ac_fwd(L.ptr(x), L.ptr(y), planes, h, w, H, W, L.stream()), "bilinear_fwd")
+        ctx.shape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = gy.contiguous()
+        shape = ctx.shape
+        h, w = shape[-2:]
+        H, W = gy.shape[-2:]
+        gx = torch.empty(shape, device=gy.device, dtype=torch.float32)
+        planes = gx.numel() // (h * w) if h * w else 0
+        L.check(L.lib().ud_bilinear_ac_bwd(L.ptr(gy), L.ptr(gx), planes, h, w, H, W, L.stream()), "bilinear_bwd")
+        return gx, None, None
+
+
+def bilinear_ac(x, size):
+    return _BilinearAC.apply(x, int(size[0]), int(size[1]))
+
+
+def attn_prep(pred, x, size, norm="ortho"):
+    """Error maps (no grad; model/unidefense.py:126-134,:148) -> (spat_diff [N,C,h,w], freq_diff [N,2C,h,w/2+1])."""
+    pred = pred.detach().contiguous()
+    x = x.detach().contiguous()
+    L.require_cuda_f32(pred, x)
+    N, C = x.shape[:2]
+    h, w = int(size[0]), int(size[1])
+    sd = torch.empty(N, C, h, w, device=x.device, dtype=torch.float32)
+    fd = torch.empty(N, 2 * C, h, w // 2 + 1, device=x.device, dtype=torch.float32)
+    L.check(L.lib().ud_attn_prep(L.ptr(pred), L.ptr(x), L.ptr(sd), L.ptr(fd), N, C, pred.shape[-2], pred.shape[-1],
+                                 x.shape[-2], x.shape[-1], h, w, int(norm == "ortho"), L.stream()), "attn_prep")
+    return sd, fd
+
+
+def _rfft2_raw(x, norm_ortho, adjoint):
+    N, C, h, w = x.shape
+    xf = torch.empty(N, 2 * C, h, w // 2 + 1, device=x.device, dtype=torch.float32)
+    L.check(L.lib().ud_rfft2_cat(L.ptr(x), L.ptr(xf), N, C, h, w, norm_ortho, adjoint, L.stream()), "rfft2_cat")
+    return xf
+
+
+def _irfft2_raw(xf, mask, h, w, norm_ortho, adjoint):
+    N, C2 = xf.shape[:2]
+    y = torch.empty(N, C2 // 2, h, w, device=xf.device, dtype=torch.float32)
+    L.check(L.lib().ud_irfft2_cat(L.ptr(xf), L.ptr(mask), L.ptr(y), N, C2 // 2, h, w, norm_ortho, adjoint, L.stream()),
+            "irfft2_cat")
+    return y
+
+
+class _Rfft2Cat(torch.autograd.Function):
+    """cat([re, im], 1) of torch.fft.rfft2 (model/unidefense.py:135-136); backward = fft_r2c_backward."""
+
+    @staticmethod
+    def forward(ctx, x, norm_ortho):
+        x = x.contiguous()
+        L.require_cuda_f32(x)
+        ctx.norm_ortho = norm_ortho
+        ctx.hw = tuple(x.shape[-2:])
+        return _rfft2_raw(x, norm_ortho, 0)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w = ctx.hw
+        return _irfft2_raw(g.contiguous(), None, h, w, ctx.norm_ortho, 1), None
+
+
+def rfft2_cat(x, norm="ortho"):
+    return _Rfft2Cat.apply(x, int(norm == "ortho"))
+
+
+class _Irfft2Cat(torch.autograd.Function):
+    """irfft2(complex(*tensor_split(xf, 2, 1)), s=(h, w)) (model/unidefense.py:142-145); backward = fft_c2r_backward."""
+
+    @staticmethod
+    def forward(ctx, xf, h, w, norm_ortho):
+        xf = xf.contiguous()
+        L.require_cuda_f32(xf)
+        if xf.shape[-2] != h or xf.shape[-1] != w // 2 + 1 or xf.shape[1] % 2:
+            raise ValueError(f"irfft2_cat: spectrum {tuple(xf.shape)} does not match s=({h},{w})")
+        ctx.norm_ortho = norm_ortho
+        return _irfft2_raw(xf, None, h, w, norm_ortho, 0)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return _rfft2_raw(gy.contiguous(), ctx.norm_ortho, 1), None, None, None
+
+
+def irfft2_cat(xf, size, norm="ortho"):
+    return _Irfft2Cat.apply(xf, int(size[0]), int(size[1]), int(norm == "ortho"))
+
+
+class _AttnFuse(torch.autograd.Function):
+    """out = (1-s)*smask*emb + s*ff + res, s = sigmoid(fuse_coef) (model/unidefense.py:153-155).
+    res=None means the residual is emb itself (dropout inactive)."""
+
+    @staticmethod
+    def forward(ctx, emb, smask, ff, res, fuse_coef):
+        emb, smask, ff = emb.contiguous(), smask.contiguous(), ff.contiguous()
+        res = None if res is None else res.contiguous()
+        coef = fuse_coef.reshape(1).contiguous()
+        L.require_cuda_f32(emb, smask, ff, res, coef)
+        N, C = emb.shape[:2]
+        HW = emb.shape[2] * emb.shape[3]
+        out = torch.empty_like(emb)
+        L.check(L.lib().ud_attn_fuse_fwd(L.ptr(emb), L.ptr(smask), L.ptr(ff), L.ptr(res), L.ptr(coef), L.ptr(out),
+                                         N, C, HW, L.stream()), "attn_fuse_fwd")
+        ctx.save_for_backward(emb, smask, ff, coef)
+        ctx.res_is_emb = res is None
+        ctx.coef_shape = fuse_coef.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        emb, smask, ff, coef = ctx.saved_tensors
+        g = g.contiguous()
+        N, C = emb.shape[:2]
+        HW = emb.shape[2] * emb.shape[3]
+        lib = L.lib()
+        g_emb, g_ff = torch.empty_like(emb), torch.empty_like(ff)
+        g_smask = torch.empty_like(smask)
+        g_coef = torch.empty(1, device=emb.device, dtype=torch.float32)
+        ws = L.workspace(lib.ud_attn_fuse_bwd_workspace_bytes(N, HW), emb.device)
+        L.check(lib.ud_attn_fuse_bwd(L.ptr(emb), L.ptr(smask), L.ptr(ff), L.ptr(g), L.ptr(coef), L.ptr(g_emb),
+                                     L.ptr(g_ff), L.ptr(g_smask), L.ptr(g_coef), L.ptr(ws), ws.numel(), N, C, HW,
+                                     int(ctx.res_is_emb), L.stream()), "attn_fuse_bwd")
+        return g_emb, g_smask, g_ff, (None if ctx.res_is_emb else g), g_coef.reshape(ctx.coef_shape)
+
+
+def attn_fuse(emb, smask, ff, res, fuse_coef):
+    return _AttnFuse.apply(emb, smask, ff, res, fuse_coef)
+
+
+# ------------------------------------------------------------------------------------------
+# a5 / a6: dynamic filters -- everything after layer1's conv
+# ------------------------------------------------------------------------------------------
+def bn_local_stats(proj):
+    """-> (mean [C], m2 [C]) of proj [N,C,h,w] over (N,h,w); m2 = sum (x-mean)^2."""
+    N, C = proj.shape[:2]
+    HW = proj.shape[2] * proj.shape[3]
+    mean = torch.empty(C, device=proj.device, dtype=torch.float32)
+    m2 = torch.empty(C, device=proj.device, dtype=torch.float32)
+    L.check(L.lib().ud_bn_stats(L.ptr(proj), L.ptr(mean), L.ptr(m2), N, C, HW, L.stream()), "bn_stats")
+    return mean, m2
+
+
+class _DyfiMask(torch.autograd.Function):
+    """BN-apply + act + channel mean/max + cat(diff) + conv1x1 + sigmoid (+ mask*x)
+    (model/modules.py:94-104, :123-133).  mean/rstd are the (possibly cross-rank) BN statistics;
+    `count` = global N*h*w in training (batch statistics take part in the backward), 0 in eval.
+    `stat_reduce` (optional callable) sums a [2, C] tensor over ranks (SyncBatchNorm backward)."""
+
+    @staticmethod
+    def forward(ctx, proj, mean, rstd, gamma, beta, diff, w2, x, act, count, want_out, stat_reduce):
+        proj, diff = proj.contiguous(), diff.contiguous()
+        x = x.contiguous()
+        w2f = w2.reshape(-1).contiguous()
+        L.require_cuda_f32(proj, mean, rstd, gamma, beta, diff, w2f, x)
+        N, Cp, h, w = proj.shape
+        HW, D, Cx = h * w, diff.shape[1], x.shape[1]
+        if w2f.numel() != 2 + D:
+            raise ValueError(f"dyfi_mask: layer2 weight has {w2f.numel()} inputs, expected {2 + D}")
+        dev = proj.device
+        mask = torch.empty(N, 1, h, w, device=dev, dtype=torch.float32)
+        out = torch.empty_like(x) if want_out else None
+        pmean = torch.empty(N, HW, device=dev, dtype=torch.float32)
+        pmax = torch.empty(N, HW, device=dev, dtype=torch.float32)
+        argmax = torch.empty(N, HW, device=dev, dtype=torch.int32)
+        L.check(L.lib().ud_dyfi_mask_fwd(L.ptr(proj), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), L.ptr(diff),
+                                         L.ptr(w2f), L.ptr(x), L.ptr(mask), L.ptr(out), L.ptr(pmean), L.ptr(pmax),
+                                         L.ptr(argmax), N, Cp, D, Cx, HW, act, L.stream()), "dyfi_mask_fwd")
+        ctx.save_for_backward(proj, mean, rstd, gamma, beta, diff, w2f, x, mask, pmean, pmax, argmax)
+        ctx.act, ctx.count, ctx.want_out, ctx.stat_reduce = act, count, want_out, stat_reduce
+        ctx.w2_shape = w2.shape
+        if want_out:
+            return mask, out
+        return mask, None
+
+    @staticmethod
+    def backward(ctx, g_mask, g_out):
+        proj, mean, rstd, gamma, beta, diff, w2f, x, mask, pmean, pmax, argmax = ctx.saved_tensors
+        N, Cp, h, w = proj.shape
+        HW, D, Cx = h * w, diff.shape[1], x.shape[1]
+        lib = L.lib()
+        dev = proj.device
+        g_mask = None if g_mask is None else g_mask.contiguous()
+        g_out = None if (g_out is None or not ctx.want_out) else g_out.contiguous()
+        g_x = torch.empty_like(x) if g_out is not None else None
+        dz = torch.empty_like(proj)
+        g_w2 = torch.empty(2 + D, device=dev, dtype=torch.float32)
+        ws = L.workspace(lib.ud_dyfi_mask_bwd_workspace_bytes(N, HW), dev)
+        L.check(lib.ud_dyfi_mask_bwd(L.ptr(proj), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), L.ptr(diff),
+                                     L.ptr(w2f), L.ptr(x), L.ptr(mask), L.ptr(pmean), L.ptr(pmax), L.ptr(argmax),
+                                     L.ptr(g_mask), L.ptr(g_out), L.ptr(g_x), L.ptr(dz), L.ptr(g_w2), L.ptr(ws),
+                                     ws.numel(), N, Cp, D, Cx, HW, ctx.act, L.stream()), "dyfi_mask_bwd")
+        sums = torch.empty(2, Cp, device=dev, dtype=torch.float32)
+        L.check(lib.ud_bn_bwd_reduce(L.ptr(dz), L.ptr(proj), L.ptr(mean), L.ptr(rstd), L.ptr(sums[0]), L.ptr(sums[1]),
+                                     N, Cp, HW, L.stream()), "bn_bwd_reduce")
+        g_beta, g_gamma = sums[0].clone(), sums[1].clone()      # local sums: DDP averages parameter grads
+        if ctx.stat_reduce is not None and ctx.count:
+            sums = ctx.stat_reduce(sums)
+        g_proj = torch.empty_like(proj)
+        inv_count = 1.0 / ctx.count if ctx.count else 0.0
+        L.check(lib.ud_bn_bwd_apply(L.ptr(dz), L.ptr(proj), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(sums[0]),
+                                    L.ptr(sums[1]), inv_count, L.ptr(g_proj), N, Cp, HW, L.stream()), "bn_bwd_apply")
+        return (g_proj, None, None, g_gamma if gamma is not None else None, g_beta if beta is not None else None,
+                None, g_w2.reshape(ctx.w2_shape), g_x, None, None, None, None)
+
+
+def dyfi_mask(proj, mean, rstd, gamma, beta, diff, w2, x, act="swish", count=0, want_out=True, stat_reduce=None):
+    """-> (mask [N,1,h,w], out = mask*x or None)."""
+    return _DyfiMask.apply(proj, mean, rstd, gamma, beta, diff, w2, x, ACT_CODES[act], int(count), bool(want_out),
+                           stat_reduce)
+
+
+# ------------------------------------------------------------------------------------------
+# a9-a11: losses (forward also produces the gradient; backward is a scalar multiply)
+# ------------------------------------------------------------------------------------------
+class _Triplet(torch.autograd.Function):
+    """AsymmetricalWeightedTripletLoss.forward (loss/triplet_loss.py:75-82)."""
+
+    @staticmethod
+    def forward(ctx, feat, labels):
+        feat = feat.contiguous()
+        L.require_cuda_f32(feat)
+        if labels.dtype != torch.int64 or not labels.is_cuda:
+            raise RuntimeError("triplet: labels must be a CUDA int64 tensor")
+        labels = labels.contiguous()
+        N, c = feat.shape
+        if labels.numel() != N:
+            raise ValueError("triplet: labels/feat batch mismatch")
+        loss = torch.empty((), device=feat.device, dtype=torch.float32)
+        g = torch.empty_like(feat) if ctx.needs_input_grad[0] else None
+        L.check(L.lib().ud_triplet_fwd(L.ptr(feat), L.ptr(labels), L.ptr(loss), L.ptr(g), N, c, L.stream()), "triplet")
+        ctx.save_for_backward(g)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        (g,) = ctx.saved_tensors
+        return g * gl, None
+
+
+def triplet_loss(feat, labels):
+    return _Triplet.apply(feat, labels)
+
+
+class _Factorization(torch.autograd.Function):
+    """FactorizationLoss.forward (loss/calib_loss.py:17-28)."""
+
+    @staticmethod
+    def forward(ctx, a, b, off_w, eps):
+        a, b = a.contiguous(), b.detach().contiguous()
+        L.require_cuda_f32(a, b)
+        N, F_ = a.shape
+        if tuple(b.shape) != (N, F_):
+            raise ValueError("factorization: emb_a / emb_b shapes differ")
+        lib = L.lib()
+        loss = torch.empty((), device=a.device, dtype=torch.float32)
+        g = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        ws = L.workspace(lib.ud_factorization_workspace_bytes(N, F_), a.device)
+        L.check(lib.ud_factorization_fwd(L.ptr(a), L.ptr(b), L.ptr(loss), L.ptr(g), L.ptr(ws), ws.numel(), N, F_,
+                                         float(off_w), float(eps), L.stream()), "factorization")
+        ctx.save_for_backward(g)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        (g,) = ctx.saved_tensors
+        return g * gl, None, None, None
+
+
+def factorization_loss(emb_a, emb_b, off_diag_weight=0.005, eps=1e-6):
+    return _Factorization.apply(emb_a, emb_b, off_diag_weight, eps)
+
+
+class _MaskKL(torch.autograd.Function):
+    """KLDivLoss(batchmean, log_target)(log_softmax(pred.flat), log_softmax(gt.flat))
+    (engine/abstract_engine.py:333-346)."""
+
+    @staticmethod
+    def forward(ctx, pred, gt):
+        shape = pred.shape
+        N = shape[0]
+        p = pred.reshape(N, -1).contiguous()
+        q = gt.detach().reshape(N, -1).contiguous()
+        L.require_cuda_f32(p, q)
+        lib = L.lib()
+        loss = torch.empty((), device=p.device, dtype=torch.float32)
+        g = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        ws = L.workspace(lib.ud_mask_kl_workspace_bytes(N), p.device)
+        L.check(lib.ud_mask_kl_fwd(L.ptr(p), L.ptr(q), L.ptr(loss), L.ptr(g), L.ptr(ws), ws.numel(), N, p.shape[1],
+                                   L.stream()), "mask_kl")
+        ctx.save_for_backward(g)
+        ctx.shape = shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        (g,) = ctx.saved_tensors
+        return (g * gl).reshape(ctx.shape), None
+
+
+def mask_kl_loss(mask_pred, mask_gt):
+    return _MaskKL.apply(mask_pred, mask_gt)
