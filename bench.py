@@ -1,0 +1,344 @@
+#!/usr/bin/env python3
+"""Benchmark of the UniDefense dual-space reconstruction path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                    # our arm, 1 GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W     # N GPUs, one rank per GPU (NCCL)
+    python bench.py --impl reference --steps 3 --warmup 1             # reference arm: CPU port on the host cores
+
+A "step" is one training step of the drop-in UniDefenseModelEb4 (EfficientNet-B4, 380x380, per-GPU
+batch 32, bf16 autocast for the stock-torch backbone and dense convs, fp32 hot-path kernels) on synthetic
+face tensors: forward, the engine's first-pass loss (engine/abstract_engine.py:215-267), backward
+(+ NCCL gradient all-reduce under DDP, SyncBatchNorm as the engines wrap it) and the AdamW(amsgrad)
+update of the config template.  Rank 0 prints ONE JSON line (see README / DESIGN.md for the keys).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+LAMBDAS = dict(triplet=0.1, recons=0.1, freq=1.0, mask=0.1, fac=0.1)   # config_template/forgery/model_udeb4.yml:12-16
+ARCH = {"eb4": ("UDEB4", dict(extractor="efficientnet-b4", num_classes=2, drop_rate=0.2), 380, 32),
+        "r18": ("UDR18", dict(num_classes=2, drop_rate=0.5), 256, 32),
+        "r50": ("UDR50", dict(extractor="resnet50", num_classes=2, drop_rate=0.5), 256, 64)}
+METRIC = "train samples/sec (fwd+bwd)"
+
+
+def peaks():
+    fn = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(fn):
+        return json.load(open(fn)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def synth(n, res, rank, device=None, pin=False):
+    g = torch.Generator().manual_seed(1234 + rank)
+    x = torch.rand(n, 3, res, res, generator=g) * 2 - 1
+    labels = torch.tensor([0] * (n // 2) + [1] * (n - n // 2), dtype=torch.int64)
+    if pin:
+        x, labels = x.pin_memory(), labels.pin_memory()
+    if device is not None:
+        x, labels = x.to(device), labels.to(device)
+    return x, labels
+
+
+def init_live(model):
+    """make every branch numerically live (sf_coef -10 / fuse_coef 0 would hide the FFT paths)."""
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("sf_coef"):
+                p.fill_(0.0)
+            elif n.endswith("fuse_coef"):
+                p.fill_(0.3)
+            elif p.ndim == 1 and n.endswith("weight"):          # every BN / IN gamma
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+    return model
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic bytes per step of each hot-path op (DESIGN.md "kernels"; SURVEY.md §8d formulas)
+# ---------------------------------------------------------------------------------------------
+def decoder_planes(arch, R):
+    """(channels, side) of every InstanceNorm+act plane and the side of the tanh output."""
+    if arch == "eb4":
+        f = -(-R // 16)            # stride-16 feature, TF-SAME padding: ceil
+        return [(80, f), (80, 2 * f), (80, 2 * f), (40, 2 * f), (40, 4 * f), (40, 4 * f), (20, 4 * f), (20, 8 * f),
+                (20, 8 * f)], 8 * f
+    if arch == "r18":
+        f = -(-R // 8)
+        return [(128, f), (128, 2 * f), (128, 2 * f), (64, 2 * f), (64, 4 * f), (32, 4 * f)], 4 * f
+    f = -(-R // 16)
+    return [(256, f), (256, 2 * f), (256, 2 * f), (128, 2 * f), (128, 4 * f), (128, 4 * f), (64, 4 * f), (64, 8 * f),
+            (32, 8 * f)], 8 * f
+
+
+def alg_bytes(arch, N, R, n_real):
+    """Compulsory fp32 HBM bytes per step of each op group: every tensor crossing the group boundary read
+    once + written once."""
+    planes, h = decoder_planes(arch, R)
+    E = sum(c * s * s for c, s in planes)
+    img, dec = 3 * R * R * 4, 3 * h * h * 4
+    return {"in_act_fwd": N * 2 * E * 4, "in_act_bwd": N * 3 * E * 4,
+            "tanh_fwd": N * 2 * dec, "tanh_bwd": N * 3 * dec,
+            "recon_tail_fwd": N * (dec + 2 * img) + 8 * N,
+            "recon_tail_bwd": n_real * (dec + img) + N * dec}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "samples": len(sm),
+                "power_w_max": max(float(r[2]) for r in self.rows if len(r) > 2), "reasons": reasons}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_arm(arch, res, sample_n, steps, warmup):
+    from oracle import ref_model
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    name, kw, _, _ = ARCH[arch]
+    torch.manual_seed(0)
+    model = init_live(ref_model.build(arch, **kw)).train()
+    x, labels = synth(sample_n, res, 0)
+    nr = sample_n // 2
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=5e-6, amsgrad=True)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = model(x)
+        loss = ref_model.pass1_loss(out, labels, nr, LAMBDAS)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": sample_n / dt, "ms_per_step": dt * 1e3, "cores": threads, "kind": "port",
+            "sample": f"{steps} steps of {sample_n} faces at {res}x{res} (fp32, torch CPU, {threads} threads), "
+                      f"same model/loss/optimizer"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arch = args.arch
+    _, _, res, nb = ARCH[arch]
+    res = args.res or res
+    r = cpu_arm(arch, res, args.cpu_sample, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"UniDefense {ARCH[arch][0]} train step, {res}x{res}, per-GPU batch {args.batch or nb}",
+                       "note": "reference arm = CPU port of the reference (oracle/) on the host cores; bounded sample per step"},
+            "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from unidefense_b200 import _lib as L
+    from unidefense_b200 import ops
+    from unidefense_b200.model import load_model
+
+    arch = args.arch
+    name, kw, res, nb = ARCH[arch]
+    res, nb = args.res or res, args.batch or nb
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True                     # engine/abstract_engine.py:120
+    model = init_live(load_model(name)(**kw)).to(dev).train()
+    if args.channels_last:
+        model = model.to(memory_format=torch.channels_last)
+    if world > 1:                                             # engine/forgery_engine.py:142-145
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
+    else:
+        ddp = model
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.999), weight_decay=5e-6, amsgrad=True, fused=True)
+    x_host, l_host = synth(nb, res, rank, pin=True)
+    x_dev, l_dev = x_host.to(dev), l_host.to(dev)
+    nr = nb // 2
+    amp = args.dtype == "bf16"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step(x, labels):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            if args.channels_last:
+                x = x.contiguous(memory_format=torch.channels_last)
+            out = ddp(x)
+        ld = out["loss_dict"]
+        tri = sum(ops.triplet_loss(f, labels) for f in ld["triplet"])
+        loss = (F.cross_entropy(out["cls_out"].float(), labels) + LAMBDAS["mask"] * ld["freq_mask"].mean()
+                + LAMBDAS["mask"] * ld["spat_mask"].mean() + LAMBDAS["triplet"] * tri
+                + LAMBDAS["recons"] * ld["spatial"][:nr].mean() + LAMBDAS["freq"] * ld["freq"][:nr].mean())
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x_dev, l_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.PROFILE = {}
+    launches0 = L.lib().ud_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        flush.zero_()                                          # L2 flush between timed iterations
+        step(x_dev, l_dev)
+    e1.record()
+    barrier()
+    launches = L.lib().ud_launch_count() - launches0
+    prof = L.profile_summary()
+    L.PROFILE = None
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.summary()
+
+    # end to end through the public API with HOST buffers: pinned H2D of the batch + D2H of the loss every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        loss = step(x_host.to(dev, non_blocking=True), l_host.to(dev, non_blocking=True))
+        loss_host = loss.item()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        ab = alg_bytes(arch, nb, res, nr)
+        ops_ms = {k: v[1] / args.steps for k, v in prof.items()}
+        timed = {k: (ab[k] / (ops_ms[k] * 1e-3) / 1e9) for k in ab if k in ops_ms and ops_ms[k] > 0}
+        dom = max((k for k in ops_ms if k in ab), key=lambda k: ops_ms[k], default=None)
+        roof = None
+        if dom:
+            ach = timed[dom]
+            roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "peak_kind": pk_kind,
+                    "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4), "traffic": TRAFFIC.get(dom),
+                    "alg_bytes_per_launch": ab[dom] // max(prof[dom][0] // args.steps, 1),
+                    "ms_per_step_in_kernel": round(ops_ms[dom], 4)}
+        hot_ms = sum(ops_ms.values())
+        line = {"metric": METRIC, "value": round(nb * world / (ms * 1e-3), 2), "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": f"UniDefense {name} train step (fwd + engine pass-1 loss + bwd + AdamW amsgrad), "
+                                       f"{res}x{res}, per-GPU batch {nb}, random init",
+                           "hot_path_dtype": "f32", "backbone": f"stock torch, {args.dtype} autocast"
+                                       + (", channels_last" if args.channels_last else ""),
+                           "parallelism": f"dp{world}" + (" (DDP + SyncBatchNorm, NCCL)" if world > 1 else ""),
+                           "l2": "256 MB buffer written between timed iterations; per-step activations >> 126 MB L2"},
+                "clocks": clocks,
+                "e2e": {"value": round(nb * world / (e2e_ms * 1e-3), 2), "unit": "samples/s",
+                        "h2d_bytes_per_step": x_host.numel() * 4 + l_host.numel() * 8, "d2h_bytes_per_step": 4,
+                        "ms_per_step": round(e2e_ms, 3), "last_loss": loss_host},
+                "gpu_launches": int(launches),
+                "roofline": roof,
+                "hot_path": {"kernel_ms_per_step": round(hot_ms, 3), "share_of_step": round(hot_ms / ms, 4),
+                             "ops_ms_per_step": {k: round(v, 4) for k, v in sorted(ops_ms.items(), key=lambda kv: -kv[1])},
+                             "ops_gbs": {k: round(v, 1) for k, v in timed.items()}}}
+        if world == 1 and not args.no_cpu_baseline:
+            c = cpu_arm(arch, res, args.cpu_sample, 2, 1)
+            line["cpu_baseline"] = {"value": round(c["value"], 3), "unit": "samples/s", "cores": c["cores"],
+                                    "kind": c["kind"], "sample": c["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram bytes per launch from the committed `ncu --set full` captures (profiles/), None until captured
+TRAFFIC = {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="eb4", choices=list(ARCH))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--res", type=int, default=0)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--channels-last", action="store_true", default=False)
+    ap.add_argument("--cpu-sample", type=int, default=4, help="faces per CPU step of the reference / cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,8 @@ typedef struct CUstream_st* cudaStream_t;
 
 UD_API const char* ud_last_error(void);
 UD_API int ud_version(void);
+/* Kernels launched by this library since load (process-wide, monotonic): bench.py's gpu_launches. */
+UD_API long long ud_launch_count(void);
 /* 1 when n-point line FFTs are supported (prime factors <= 23, n <= UD_FFT_MAX_N). */
 UD_API int ud_fft_size_supported(int n);
 
@@ -157,6 +159,18 @@ UD_API int ud_factorization_fwd(const float* emb_a, const float* emb_b, float* l
 UD_API size_t ud_mask_kl_workspace_bytes(int N);
 UD_API int ud_mask_kl_fwd(const float* pred, const float* gt, float* loss, float* g_pred, void* ws, size_t ws_bytes,
                           int N, int M, cudaStream_t stream);
+
+/* nn.KLDivLoss(reduction="batchmean", log_target=True) (loss/__init__.py:17) with the engine's call
+ * signature: both arguments are log-probabilities [N,M] (workspace: ud_mask_kl_workspace_bytes).  */
+UD_API int ud_kl_div_log_target_fwd(const float* log_pred, const float* log_target, float* loss, float* g_pred,
+                                    void* ws, size_t ws_bytes, int N, int M, cudaStream_t stream);
+
+/* ---- a16: stencil / resampling perturbations (no grad) ---------------------------------------------
+ * random_blur (model/modules.py:15-16): torchvision gaussian_blur 5x5, sigma 1.1, reflect padding.   */
+UD_API int ud_gaussian_blur5(const float* x, float* y, int planes, int H, int W, cudaStream_t stream);
+/* downscale (model/modules.py:19-21): nearest by `bottleneck_scale`, then nearest back to HxW.       */
+UD_API int ud_downscale_nearest(const float* x, float* y, int planes, int H, int W, float bottleneck_scale,
+                                cudaStream_t stream);
 
 #ifdef __cplusplus
 }

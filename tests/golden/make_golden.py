@@ -277,9 +277,64 @@ def make_path(ref, arch):
     return fix
 
 
+def make_full(ref, arch):
+    """Whole reference model (backbone included) with EVERY weight regenerated from its name, train mode,
+    stochastic ops off: pins our stock-torch backbone + hot path end to end."""
+    import torch.nn.functional as F
+    if arch == "eb4":
+        model = ref.unidefense.UniDefenseModelEb4("efficientnet-b4", num_classes=2, drop_rate=0.0, drop_connect_rate=0.0)
+        R, N = 128, 4
+    elif arch == "r18":
+        model = ref.unidefense.UniDefenseModelRes18(drop_rate=0.0)
+        R, N = 96, 4
+    else:
+        model = ref.unidefense.UniDefenseModelRes50(drop_rate=0.0)
+        R, N = 64, 4
+    P.fill_state_dict_(model, salt=5)
+    model.train()
+    x = T(f"full_x_{arch}", (N, 3, R, R))
+    labels = torch.tensor([0] * (N // 2) + [1] * (N // 2))
+    orig_dropout = F.dropout
+    F.dropout = lambda t, p=0.5, training=True, inplace=False: t * 1.0
+    try:
+        out = model(x)
+    finally:
+        F.dropout = orig_dropout
+    ld = out["loss_dict"]
+    nr = N // 2
+    tri = ref.loss.LOSSES["aw_triplet"]
+    ce = torch.nn.CrossEntropyLoss()
+    tri_loss = sum(tri(f, labels) for f in ld["triplet"])
+    loss = (ce(out["cls_out"], labels) + 0.1 * ld["freq_mask"].mean() + 0.1 * ld["spat_mask"].mean() + 0.1 * tri_loss
+            + 0.1 * ld["spatial"][:nr].mean() + 1.0 * ld["freq"][:nr].mean())
+    named = [(n_, p_) for n_, p_ in model.named_parameters() if p_.requires_grad]
+    gs = torch.autograd.grad(loss, [p_ for _, p_ in named], allow_unused=True)
+    pg = {}
+    for (n_, p_), g in zip(named, gs):
+        if g is None:
+            pg[n_] = None
+            continue
+        idx = P.sample_indices(p_.numel(), 16, n_)
+        pg[n_] = {"norm": g.norm().item(), "sample": g.flatten()[idx].clone()}
+    sd_after = model.state_dict()
+    bn_after = {k: v.clone() for k, v in sd_after.items() if k.endswith("running_mean")
+                and k.startswith(("bottleneck", "freq_filter", "spat_filter"))}
+    return {"arch": arch, "R": R, "N": N, "labels": labels, "cls_out": out["cls_out"].detach(),
+            "rec_sample": out["rec"].detach()[:, :, ::7, ::5].clone(), "spatial": ld["spatial"].detach(),
+            "freq": ld["freq"].detach(), "freq_mask": ld["freq_mask"].detach(), "spat_mask": ld["spat_mask"].detach(),
+            "factorization": ld["factorization"].detach(), "triplet_feats": [t.detach() for t in ld["triplet"]],
+            "loss": loss.detach(), "param_grads": pg, "bn_after": bn_after,
+            "state_dict_shapes": {k: tuple(v.shape) for k, v in sd_after.items()}}
+
+
 def main():
     ref = ref_loader.load()
-    which = sys.argv[1:] or ["ops", "eb4", "r18", "r50"]
+    which = sys.argv[1:] or ["ops", "eb4", "r18", "r50", "full"]
+    if "full" in which:
+        for arch in ("eb4", "r18", "r50"):
+            fn = os.path.join(HERE, f"full_{arch}.pt")
+            torch.save(make_full(ref, arch), fn)
+            print("wrote", fn, os.path.getsize(fn))
     if "ops" in which:
         torch.save(make_ops(ref), os.path.join(HERE, "ops.pt"))
         print("wrote ops.pt", os.path.getsize(os.path.join(HERE, "ops.pt")))

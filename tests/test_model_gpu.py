@@ -1,0 +1,137 @@
+"""Model-level parity on the GPU: (1) the hot path driven with the boundary tensors captured inside the
+reference model classes (path_*.pt); (2) the whole drop-in model, backbone included, against the whole
+reference model with name-regenerated weights (full_*.pt)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import procedural as P
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CTOR = {"eb4": ("UDEB4", dict(extractor="efficientnet-b4", num_classes=2, drop_rate=0.0, drop_connect_rate=0.0)),
+        "r18": ("UDR18", dict(num_classes=2, drop_rate=0.0)),
+        "r50": ("UDR50", dict(extractor="resnet50", num_classes=2, drop_rate=0.0))}
+
+
+def close(a, b, rtol=1e-3, atol=None):
+    b = b.detach()
+    scale = float(b.abs().max()) if b.numel() else 1.0
+    atol = (1e-4 * max(scale, 1e-6)) if atol is None else atol
+    torch.testing.assert_close(a.detach().cpu().to(b.dtype), b, rtol=rtol, atol=atol)
+
+
+def _build(arch, salt, hot_only):
+    from unidefense_b200.model import load_model
+    name, kw = CTOR[arch]
+    model = load_model(name)(**kw)
+    P.fill_state_dict_(model, prefix_filter=P.is_hot if hot_only else None, salt=salt)
+    return model.cuda().train()
+
+
+@pytest.fixture()
+def no_dropout(monkeypatch):
+    monkeypatch.setattr(F, "dropout", lambda t, p=0.5, training=True, inplace=False: t * 1.0)
+
+
+def test_hot_path_against_reference_model(golden_path, no_dropout):
+    from unidefense_b200 import ops
+    fix = golden_path
+    arch = fix["arch"]
+    model = _build(arch, 3, True)
+    feat = fix["feat"].cuda().requires_grad_()
+    emb = fix["emb"].cuda().requires_grad_()
+    x, labels = fix["x"].cuda(), fix["labels"].cuda()
+    nblocks = 2 if arch == "r18" else 3
+    ntri = 2 if arch == "eb4" else 1
+    y, dec_outs, tris = feat, [], []
+    for i in range(1, nblocks + 1):
+        blk = getattr(model, f"dec_block{i}")
+        if i <= ntri:
+            y, t = blk.forward_with_mean(y)
+            tris.append(t)
+        else:
+            y = blk(y)
+        dec_outs.append(y)
+        close(y, fix[f"dec_out{i}"])
+    att = model.attention(dec_outs[-1].detach(), x, emb)
+    close(att["freq_mask"], fix["freq_mask"]); close(att["spat_mask"], fix["spat_mask"]); close(att["out"], fix["att_out"])
+    rec, spatial, freq = ops.recon_tail(dec_outs[-1], x)
+    close(rec, fix["rec"]); close(spatial, fix["spatial"], rtol=1e-4); close(freq, fix["freq"], rtol=1e-4)
+    tri_feats = [feat.mean(dim=(-2, -1))] + tris
+    for a, b in zip(tri_feats, fix["triplet_feats"]):
+        close(a, b)
+    tri = sum(ops.triplet_loss(f, labels) for f in tri_feats)
+    close(tri, fix["triplet_loss"], rtol=1e-4)
+    nr = int((fix["labels"] == 0).sum())
+    loss = (0.1 * att["freq_mask"].mean() + 0.1 * att["spat_mask"].mean() + 0.1 * tri + 0.1 * spatial[:nr].mean()
+            + 1.0 * freq[:nr].mean() + (att["out"] * fix["r_att"].cuda()).sum())
+    close(loss, fix["loss"], rtol=1e-4)
+    names = list(fix["param_grads"])
+    params = dict(model.named_parameters())
+    gs = torch.autograd.grad(loss, [feat, emb] + [params[n] for n in names])
+    close(gs[0], fix["g_feat"], rtol=2e-3, atol=2e-4 * float(fix["g_feat"].abs().max()))
+    close(gs[1], fix["g_emb"], rtol=2e-3, atol=2e-4 * float(fix["g_emb"].abs().max()))
+    for n, g in zip(names, gs[2:]):
+        ref = fix["param_grads"][n]
+        assert abs(g.norm().item() - ref["norm"]) <= 2e-3 * ref["norm"] + 1e-7, n
+        idx = P.sample_indices(g.numel(), 64, n)
+        close(g.flatten()[idx.cuda()], ref["sample"], rtol=5e-3, atol=2e-3 * float(ref["sample"].abs().max()) + 1e-8)
+    sd = model.state_dict()
+    for k, v in fix["bn_after"].items():
+        close(sd[k], v, rtol=1e-4)
+
+
+@pytest.mark.parametrize("arch", ["eb4", "r18", "r50"])
+def test_full_model_against_reference(arch, no_dropout):
+    from unidefense_b200 import ops
+    fix = torch.load(os.path.join(GOLDEN, f"full_{arch}.pt"), weights_only=False)
+    model = _build(arch, 5, False)
+    x = P.tensor_for(f"in:full_x_{arch}", (fix["N"], 3, fix["R"], fix["R"]), "unit").cuda()
+    labels = fix["labels"].cuda()
+    out = model(x)
+    ld = out["loss_dict"]
+    assert set(out) == {"cls_out", "rec", "loss_dict"}
+    assert set(ld) == {"factorization", "triplet", "freq_mask", "spat_mask", "spatial", "freq"}
+    close(ld["spatial"], fix["spatial"]); close(ld["freq"], fix["freq"])
+    close(ld["freq_mask"], fix["freq_mask"]); close(ld["spat_mask"], fix["spat_mask"])
+    close(out["rec"][:, :, ::7, ::5], fix["rec_sample"])
+    for a, b in zip(ld["triplet"], fix["triplet_feats"]):
+        close(a, b)
+    close(ld["factorization"], fix["factorization"], rtol=5e-3, atol=5e-3)
+    close(out["cls_out"], fix["cls_out"], rtol=5e-3, atol=5e-3)
+    nr = fix["N"] // 2
+    tri = sum(ops.triplet_loss(f, labels) for f in ld["triplet"])
+    loss = (F.cross_entropy(out["cls_out"], labels) + 0.1 * ld["freq_mask"].mean() + 0.1 * ld["spat_mask"].mean()
+            + 0.1 * tri + 0.1 * ld["spatial"][:nr].mean() + 1.0 * ld["freq"][:nr].mean())
+    close(loss, fix["loss"], rtol=1e-3)
+    loss.backward()
+    bad = []
+    for n, p in model.named_parameters():
+        ref = fix["param_grads"].get(n)
+        if not p.requires_grad:
+            continue
+        assert ref is not None, f"{n}: reference has no gradient entry"
+        assert p.grad is not None, f"{n}: no gradient (DDP find_unused_parameters=False would hang)"
+        gn = p.grad.norm().item()
+        if abs(gn - ref["norm"]) > 2e-2 * ref["norm"] + 1e-6:
+            bad.append((n, gn, ref["norm"]))
+    assert not bad, bad[:8]
+    sd = model.state_dict()
+    for k, v in fix["bn_after"].items():
+        close(sd[k], v, rtol=1e-3)
+
+
+def test_eval_mode_and_dtypes():
+    """validate()/test() path (engine/forgery_engine.py:343-350): eval mode, no grad, softmax over cls_out."""
+    model = _build("r18", 5, False).eval()
+    x = (torch.rand(3, 3, 64, 64, device="cuda") * 2 - 1)
+    with torch.no_grad():
+        out = model(x)
+    assert out["cls_out"].shape == (3, 2) and out["rec"].shape == x.shape
+    assert out["loss_dict"]["freq_mask"].shape == (3, 1, 4, 3) and out["loss_dict"]["spat_mask"].shape == (3, 1, 4, 4)
+    assert torch.isfinite(torch.softmax(out["cls_out"], 1)).all()
+    out2 = model(x)
+    torch.testing.assert_close(out2["cls_out"], out["cls_out"])      # deterministic

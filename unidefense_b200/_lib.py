@@ -6,6 +6,7 @@ a contiguous CUDA fp32 tensor, the call fails loudly.
 import ctypes
 import os
 import threading
+import types
 
 import torch
 
@@ -23,6 +24,7 @@ c_sz = ctypes.c_size_t
 SIGNATURES = {
     "ud_last_error": (ctypes.c_char_p, []),
     "ud_version": (c_i, []),
+    "ud_launch_count": (ctypes.c_longlong, []),
     "ud_fft_size_supported": (c_i, [c_i]),
     "ud_recon_tail_workspace_bytes": (c_sz, [c_i] * 6),
     "ud_recon_tail_signs_bytes": (c_sz, [c_i] * 4),
@@ -52,6 +54,9 @@ SIGNATURES = {
     "ud_factorization_fwd": (c_i, [c_p] * 5 + [c_sz, c_i, c_i, c_f, c_f, c_p]),
     "ud_mask_kl_workspace_bytes": (c_sz, [c_i]),
     "ud_mask_kl_fwd": (c_i, [c_p] * 5 + [c_sz, c_i, c_i, c_p]),
+    "ud_gaussian_blur5": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
+    "ud_downscale_nearest": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_p]),
+    "ud_kl_div_log_target_fwd": (c_i, [c_p] * 5 + [c_sz, c_i, c_i, c_p]),
 }
 
 
@@ -65,18 +70,51 @@ def lib():
                         f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
                         "(or `make -C unidefense_b200/csrc`). There is no CPU/PyTorch fallback.")
                 L = ctypes.CDLL(LIB_PATH)
+                ns = types.SimpleNamespace(_cdll=L)
                 for name, (res, args) in SIGNATURES.items():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                _lib = L
+                    launches = res is c_i and len(args) > 1 and args[-1] is c_p
+                    setattr(ns, name, _timed(fn) if launches else fn)
+                _lib = ns
     return _lib
 
 
+# Optional per-op device timing (bench.py's roofline leg): when PROFILE is a dict, every C-ABI call that
+# passes through check() is bracketed by CUDA events on the launching stream: name -> [(start, end), ...].
+PROFILE = None
+_pending = []
+
+
+def _timed(fn):
+    """Wrap a stream-taking entry point so that, when profiling, a start event precedes its launches."""
+    def call(*args):
+        if PROFILE is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream())
+            _pending.append(ev)
+        return fn(*args)
+    return call
+
+
 def check(rc: int, what: str = ""):
+    if PROFILE is not None and _pending:
+        ev0 = _pending.pop()
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record(torch.cuda.current_stream())
+        PROFILE.setdefault(what, []).append((ev0, ev1))
     if rc != 0:
         msg = lib().ud_last_error().decode(errors="replace")
         raise RuntimeError(f"unidefense_b200 {what} failed (code {rc}): {msg}")
+
+
+def profile_summary():
+    """-> {op: (calls, total_ms)} after a torch.cuda.synchronize()."""
+    out = {}
+    for k, evs in (PROFILE or {}).items():
+        out[k] = (len(evs), sum(a.elapsed_time(b) for a, b in evs))
+    return out
 
 
 def ptr(t):

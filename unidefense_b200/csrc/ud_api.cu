@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -21,7 +22,12 @@ void ud_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+void ud_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long ud_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 int ud_check_launch(const char* what) {
+  ud_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     ud_set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));

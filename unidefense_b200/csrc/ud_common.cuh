@@ -12,7 +12,8 @@
 
 // thread-local last error (ud_api.cu)
 void ud_set_error(const char* fmt, ...);
-int ud_check_launch(const char* what);
+int ud_check_launch(const char* what);   // also counts the launch (ud_launch_count)
+void ud_count_launch(void);
 
 #define UD_REQUIRE(cond, code, ...)            \
   do {                                         \

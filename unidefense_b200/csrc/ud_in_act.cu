@@ -291,6 +291,7 @@ static int ia_launch(K kernel, int blocks, int cs, cudaStream_t stream, Args... 
   cfg.attrs = attr;
   cfg.numAttrs = cs > 1 ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  ud_count_launch();
   if (e != cudaSuccess) {
     ud_set_error("in_act: cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
     return UD_ERR_CUDA;

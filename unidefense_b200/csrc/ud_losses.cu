@@ -401,3 +401,35 @@ extern "C" int ud_mask_kl_fwd(const float* pred, const float* gt, float* loss, f
   ls_sum_kernel<<<1, 128, 0, stream>>>(rows, loss, N);
   return ud_check_launch("mask_kl_sum");
 }
+
+// nn.KLDivLoss(reduction="batchmean", log_target=True) on already-normalised log-probabilities, the
+// signature the engine calls (engine/abstract_engine.py:337,345): loss = sum exp(t)*(t - x) / N,
+// d loss / d x = -exp(t) / N.
+__global__ void __launch_bounds__(128)
+ls_kl_log_kernel(const float* __restrict__ x, const float* __restrict__ t, float* __restrict__ row_loss,
+                 float* __restrict__ g_x, int N, int M) {
+  __shared__ float red[33];
+  const int n = blockIdx.x;
+  float l = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const float tv = t[(long long)n * M + i], xv = x[(long long)n * M + i];
+    const float e = expf(tv);
+    l = fmaf(e, tv - xv, l);
+    if (g_x) g_x[(long long)n * M + i] = -e / (float)N;
+  }
+  l = ud_block_sum(l, red);
+  if (threadIdx.x == 0) row_loss[n] = l / (float)N;
+}
+
+extern "C" int ud_kl_div_log_target_fwd(const float* log_pred, const float* log_target, float* loss, float* g_pred,
+                                        void* ws, size_t ws_bytes, int N, int M, cudaStream_t stream) {
+  UD_REQUIRE(N >= 1 && M >= 1, UD_ERR_INVALID, "kl_div: bad shape N=%d M=%d", N, M);
+  UD_REQUIRE(log_pred && log_target && loss && ws, UD_ERR_INVALID, "kl_div: null pointer");
+  UD_REQUIRE(ws_bytes >= ud_mask_kl_workspace_bytes(N), UD_ERR_WORKSPACE, "kl_div: workspace too small");
+  float* rows = static_cast<float*>(ws);
+  ls_kl_log_kernel<<<N, 128, 0, stream>>>(log_pred, log_target, rows, g_pred, N, M);
+  int rc = ud_check_launch("kl_div");
+  if (rc != UD_OK) return rc;
+  ls_sum_kernel<<<1, 128, 0, stream>>>(rows, loss, N);
+  return ud_check_launch("kl_div_sum");
+}

@@ -138,6 +138,19 @@ class EfficientNetFeatures(nn.Module):
         self._avg_pooling = nn.AdaptiveAvgPool2d(1)
         self.num_features = head
 
+    def load_pretrained(self, weights_path: str):
+        """lukemelas-format checkpoint (model/efficientnet/utils.py:589-623): the classifier keys are
+        dropped, only SFConv-owned keys (freq_conv / sf_coef) may be missing."""
+        sd = torch.load(weights_path, map_location="cpu")
+        sd.pop("_fc.weight", None)
+        sd.pop("_fc.bias", None)
+        ret = self.load_state_dict(sd, strict=False)
+        bad = [k for k in ret.missing_keys if "sf_coef" not in k and "freq_conv" not in k]
+        if bad:
+            raise RuntimeError("Missing keys when loading pretrained weights: {}".format(bad))
+        assert not ret.unexpected_keys, "Missing keys when loading pretrained weights: {}".format(ret.unexpected_keys)
+        print("Loaded pretrained weights for efficientnet from {}".format(weights_path))
+
     def stem(self, x):
         return F.silu(self._bn0(self._conv_stem(x)))
 

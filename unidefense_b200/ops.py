@@ -420,11 +420,11 @@ def factorization_loss(emb_a, emb_b, off_diag_weight=0.005, eps=1e-6):
 
 
 class _MaskKL(torch.autograd.Function):
-    """KLDivLoss(batchmean, log_target)(log_softmax(pred.flat), log_softmax(gt.flat))
-    (engine/abstract_engine.py:333-346)."""
+    """fused=True: KLDivLoss(batchmean, log_target)(log_softmax(pred.flat), log_softmax(gt.flat))
+    (engine/abstract_engine.py:333-346).  fused=False: the bare KLDivLoss on log-probabilities."""
 
     @staticmethod
-    def forward(ctx, pred, gt):
+    def forward(ctx, pred, gt, fused=True):
         shape = pred.shape
         N = shape[0]
         p = pred.reshape(N, -1).contiguous()
@@ -434,8 +434,9 @@ class _MaskKL(torch.autograd.Function):
         loss = torch.empty((), device=p.device, dtype=torch.float32)
         g = torch.empty_like(p) if ctx.needs_input_grad[0] else None
         ws = L.workspace(lib.ud_mask_kl_workspace_bytes(N), p.device)
-        L.check(lib.ud_mask_kl_fwd(L.ptr(p), L.ptr(q), L.ptr(loss), L.ptr(g), L.ptr(ws), ws.numel(), N, p.shape[1],
-                                   L.stream()), "mask_kl")
+        fn = lib.ud_mask_kl_fwd if fused else lib.ud_kl_div_log_target_fwd
+        L.check(fn(L.ptr(p), L.ptr(q), L.ptr(loss), L.ptr(g), L.ptr(ws), ws.numel(), N, p.shape[1], L.stream()),
+                "mask_kl" if fused else "kl_div")
         ctx.save_for_backward(g)
         ctx.shape = shape
         return loss
@@ -443,8 +444,88 @@ class _MaskKL(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gl):
         (g,) = ctx.saved_tensors
-        return (g * gl).reshape(ctx.shape), None
+        return (g * gl).reshape(ctx.shape), None, None
 
 
 def mask_kl_loss(mask_pred, mask_gt):
-    return _MaskKL.apply(mask_pred, mask_gt)
+    return _MaskKL.apply(mask_pred, mask_gt, True)
+
+
+def kl_div_log_target(log_pred, log_target):
+    """nn.KLDivLoss(reduction='batchmean', log_target=True)(log_pred, log_target) for [N, M] inputs."""
+    return _MaskKL.apply(log_pred, log_target, False)
+
+
+# ------------------------------------------------------------------------------------------
+# a13-a16: perturbations (no grad)
+# ------------------------------------------------------------------------------------------
+def gaussian_blur5(x):
+    """random_blur (model/modules.py:15-16)."""
+    x = x.detach().contiguous()
+    L.require_cuda_f32(x)
+    H, W = x.shape[-2:]
+    y = torch.empty_like(x)
+    L.check(L.lib().ud_gaussian_blur5(L.ptr(x), L.ptr(y), x.numel() // (H * W), H, W, L.stream()), "gaussian_blur5")
+    return y
+
+
+def downscale_nearest(x, bottleneck_scale=0.75):
+    """downscale (model/modules.py:19-21)."""
+    x = x.detach().contiguous()
+    L.require_cuda_f32(x)
+    H, W = x.shape[-2:]
+    y = torch.empty_like(x)
+    L.check(L.lib().ud_downscale_nearest(L.ptr(x), L.ptr(y), x.numel() // (H * W), H, W, float(bottleneck_scale),
+                                         L.stream()), "downscale")
+    return y
+
+
+def freq_style_transfer(content, style, lmda):
+    """FrequencyStyleTransfer (model/modules.py:43-54); lmda [B] in [0.5, 1).
+    Library composition (cuFFT + ATen) for now; the fused sm_100a kernel is the next a13 step."""
+    L.require_cuda_f32(content, style)
+    H, W = content.shape[-2:]
+    lm = lmda.reshape(-1, 1, 1, 1).to(content)
+    fa = torch.fft.rfft2(content, norm="ortho")
+    fb = torch.fft.rfft2(style, norm="ortho")
+    mix = (lm * torch.abs(fa) + (1.0 - lm) * torch.abs(fb)) * torch.exp(1j * torch.angle(fa))
+    return torch.fft.irfft2(mix, s=(H, W), norm="ortho")
+
+
+def spatial_style_transfer(content, style, lmda):
+    """SpatialStyleTransfer (model/modules.py:59-76): exact histogram matching; lmda [B].
+    Library composition (CUB segmented sort through torch.sort) -- SURVEY.md marks the sort optional."""
+    L.require_cuda_f32(content, style)
+    B, C, H, W = content.shape
+    lm = lmda.reshape(-1, 1, 1).to(content)
+    cf = content.reshape(B, C, -1)
+    _, idx = torch.sort(cf, dim=-1)
+    vs, _ = torch.sort(style.reshape(B, C, -1), dim=-1)
+    matched = torch.empty_like(cf).scatter_(-1, idx, vs)        # == vs.gather(-1, idx.argsort(-1))
+    return (cf + (1 - lm) * matched - (1 - lm) * cf).view(B, C, H, W)
+
+
+def coral_batch(source, target):
+    """coral (utils/operation.py:20-45) for every (source[n], target[n]) pair at once, without the
+    reference's per-sample python loop (model/unidefense.py:189-191).  Keeps the reference's
+    U*sqrt(D)*Vh^T 'square root' (Appendix D); the 3x3 SVDs go through the same torch.linalg.svd."""
+    L.require_cuda_f32(source, target)
+    N, C = source.shape[:2]
+    shape = source.shape
+
+    def stats(img):
+        f = img.reshape(N, C, -1)
+        mean = f.mean(dim=-1, keepdim=True)
+        std = f.std(dim=-1, keepdim=True)
+        fn = (f - mean) / std
+        cov = fn @ fn.transpose(1, 2) + torch.eye(C, device=img.device, dtype=img.dtype)
+        return fn, mean, std, cov
+
+    def quirk_sqrt(m):
+        U, D, Vh = torch.linalg.svd(m)
+        return U @ torch.diag_embed(D.sqrt()) @ Vh.transpose(1, 2)
+
+    s_n, _, _, s_cov = stats(source)
+    _, t_mean, t_std, t_cov = stats(target)
+    m = quirk_sqrt(t_cov) @ torch.linalg.inv(quirk_sqrt(s_cov))
+    return ((m @ s_n) * t_std + t_mean).view(shape)
