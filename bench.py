@@ -182,6 +182,64 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# isolated recon path: everything downstream of the backbone features, fwd + bwd, on cached features
+# ---------------------------------------------------------------------------------------------
+RECON_MB_PER_SAMPLE = {("eb4", 380): 71.2, ("r50", 256): 91.0, ("r18", 256): 78.6, ("r18", 380): 176.1}
+
+
+def recon_path_probe(model, arch, nb, res, dev, amp, steps, flush):
+    """decoder -> attention -> rec tail -> triplet with the engine's pass-1 weights on random backbone features
+    of the config's shapes (BASELINE.md §2 'isolated recon path').  -> ms per fwd+bwd."""
+    from unidefense_b200 import ops
+    g = torch.Generator().manual_seed(99)
+    f16 = -(-res // 16)
+    shapes = {"eb4": ((160, f16), (272, -(-res // 32))), "r18": ((448, -(-res // 8)), (512, f16)),
+              "r50": ((1024, f16), (2048, -(-res // 32)))}[arch]
+    feat = torch.randn(nb, shapes[0][0], shapes[0][1], shapes[0][1], generator=g).to(dev).requires_grad_()
+    emb = torch.randn(nb, shapes[1][0], shapes[1][1], shapes[1][1], generator=g).to(dev).requires_grad_()
+    x, labels = synth(nb, res, 0, dev)
+    r_att = torch.randn(emb.shape, generator=g).to(dev) * 1e-3
+    blocks = [getattr(model, f"dec_block{i}") for i in (1, 2, 3) if hasattr(model, f"dec_block{i}")]
+    ntri = 2 if arch == "eb4" else 1
+    nr = nb // 2
+    params = [p for n, p in model.named_parameters() if n.startswith(("dec_block", "freq_filter", "spat_filter", "fuse_coef"))]
+
+    def once():
+        for p in params:
+            p.grad = None
+        feat.grad = emb.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            y, tris = feat, []
+            for i, blk in enumerate(blocks):
+                if i < ntri:
+                    y, t = blk.forward_with_mean(y)
+                    tris.append(t)
+                else:
+                    y = blk(y)
+            att = model.attention(y.detach(), x, emb)
+        rec, spatial, freq = ops.recon_tail(y.float(), x, model.freq_norm)
+        tri = sum(ops.triplet_loss(f, labels) for f in [feat.mean(dim=(-2, -1))] + tris)
+        loss = (LAMBDAS["mask"] * att["freq_mask"].mean() + LAMBDAS["mask"] * att["spat_mask"].mean()
+                + LAMBDAS["triplet"] * tri + LAMBDAS["recons"] * spatial[:nr].mean() + LAMBDAS["freq"] * freq[:nr].mean()
+                + (att["out"] * r_att).sum())
+        loss.backward()
+
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        once()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / steps
+
+
+# ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -239,6 +297,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.recon_only:
+        ms_ = recon_path_probe(model, arch, nb, res, dev, amp, args.steps, flush)
+        print(json.dumps({"recon_only_ms": ms_, "samples_per_s": nb / (ms_ * 1e-3)}), flush=True)
+        return
     for _ in range(args.warmup):
         step(x_dev, l_dev)
     barrier()
@@ -273,6 +335,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
 
+    recon_ms = None
+    if world == 1 and not args.no_recon_probe:
+        L.PROFILE = {}
+        recon_ms = recon_path_probe(model, arch, nb, res, dev, amp, max(args.steps, 5), flush)
+        recon_prof = {k: v[1] / max(args.steps, 5) for k, v in L.profile_summary().items()}
+        L.PROFILE = None
+
     if rank == 0:
         pk, pk_kind = peaks()
         ab = alg_bytes(arch, nb, res, nr)
@@ -305,6 +374,15 @@ def run_ours(args):
                 "hot_path": {"kernel_ms_per_step": round(hot_ms, 3), "share_of_step": round(hot_ms / ms, 4),
                              "ops_ms_per_step": {k: round(v, 4) for k, v in sorted(ops_ms.items(), key=lambda kv: -kv[1])},
                              "ops_gbs": {k: round(v, 1) for k, v in timed.items()}}}
+        if recon_ms is not None:
+            mb = RECON_MB_PER_SAMPLE.get((arch, res))
+            kern_ms = sum(recon_prof.values())
+            line["recon_path"] = {
+                "what": "isolated recon path fwd+bwd on cached backbone features (decoder incl. cuDNN convs, attention, "
+                        "rec tail, triplet)", "ms": round(recon_ms, 3), "samples_per_s": round(nb / (recon_ms * 1e-3), 1),
+                "our_kernels_ms": round(kern_ms, 3), "alg_mb_per_sample": mb,
+                "hbm_frac_whole_path": round(mb * 1e6 * nb / (recon_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4) if mb else None,
+                "hbm_frac_our_kernels": round(mb * 1e6 * nb / (kern_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4) if mb else None}
         if world == 1 and not args.no_cpu_baseline:
             c = cpu_arm(arch, res, args.cpu_sample, 2, 1)
             line["cpu_baseline"] = {"value": round(c["value"], 3), "unit": "samples/s", "cores": c["cores"],
@@ -331,6 +409,8 @@ def main():
     ap.add_argument("--channels-last", action="store_true", default=False)
     ap.add_argument("--cpu-sample", type=int, default=4, help="faces per CPU step of the reference / cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-recon-probe", action="store_true")
+    ap.add_argument("--recon-only", action="store_true", help="run only the isolated recon-path probe (profiling aid)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -279,52 +279,71 @@ def make_path(ref, arch):
 
 def make_full(ref, arch):
     """Whole reference model (backbone included) with EVERY weight regenerated from its name, train mode,
-    stochastic ops off: pins our stock-torch backbone + hot path end to end."""
+    stochastic ops off: pins our stock-torch backbone + hot path end to end.  The model is run twice, the
+    second time with the input perturbed by 2e-7 (about one fp32 ulp): the spread between the two runs is the
+    reference's own conditioning ("noise") per tensor, stored so the parity test can scale its tolerance --
+    deep train-mode BatchNorm on 4 samples and |.|/max/relu kinks amplify rounding differences."""
     import torch.nn.functional as F
-    if arch == "eb4":
-        model = ref.unidefense.UniDefenseModelEb4("efficientnet-b4", num_classes=2, drop_rate=0.0, drop_connect_rate=0.0)
-        R, N = 128, 4
-    elif arch == "r18":
-        model = ref.unidefense.UniDefenseModelRes18(drop_rate=0.0)
-        R, N = 96, 4
-    else:
-        model = ref.unidefense.UniDefenseModelRes50(drop_rate=0.0)
-        R, N = 64, 4
-    P.fill_state_dict_(model, salt=5)
-    model.train()
-    x = T(f"full_x_{arch}", (N, 3, R, R))
-    labels = torch.tensor([0] * (N // 2) + [1] * (N // 2))
-    orig_dropout = F.dropout
-    F.dropout = lambda t, p=0.5, training=True, inplace=False: t * 1.0
-    try:
-        out = model(x)
-    finally:
-        F.dropout = orig_dropout
-    ld = out["loss_dict"]
-    nr = N // 2
-    tri = ref.loss.LOSSES["aw_triplet"]
-    ce = torch.nn.CrossEntropyLoss()
-    tri_loss = sum(tri(f, labels) for f in ld["triplet"])
-    loss = (ce(out["cls_out"], labels) + 0.1 * ld["freq_mask"].mean() + 0.1 * ld["spat_mask"].mean() + 0.1 * tri_loss
-            + 0.1 * ld["spatial"][:nr].mean() + 1.0 * ld["freq"][:nr].mean())
-    named = [(n_, p_) for n_, p_ in model.named_parameters() if p_.requires_grad]
-    gs = torch.autograd.grad(loss, [p_ for _, p_ in named], allow_unused=True)
-    pg = {}
-    for (n_, p_), g in zip(named, gs):
-        if g is None:
-            pg[n_] = None
-            continue
-        idx = P.sample_indices(p_.numel(), 16, n_)
-        pg[n_] = {"norm": g.norm().item(), "sample": g.flatten()[idx].clone()}
-    sd_after = model.state_dict()
-    bn_after = {k: v.clone() for k, v in sd_after.items() if k.endswith("running_mean")
-                and k.startswith(("bottleneck", "freq_filter", "spat_filter"))}
-    return {"arch": arch, "R": R, "N": N, "labels": labels, "cls_out": out["cls_out"].detach(),
-            "rec_sample": out["rec"].detach()[:, :, ::7, ::5].clone(), "spatial": ld["spatial"].detach(),
-            "freq": ld["freq"].detach(), "freq_mask": ld["freq_mask"].detach(), "spat_mask": ld["spat_mask"].detach(),
-            "factorization": ld["factorization"].detach(), "triplet_feats": [t.detach() for t in ld["triplet"]],
-            "loss": loss.detach(), "param_grads": pg, "bn_after": bn_after,
-            "state_dict_shapes": {k: tuple(v.shape) for k, v in sd_after.items()}}
+
+    def run(eps):
+        if arch == "eb4":
+            model = ref.unidefense.UniDefenseModelEb4("efficientnet-b4", num_classes=2, drop_rate=0.0,
+                                                      drop_connect_rate=0.0)
+            R, N = 128, 4
+        elif arch == "r18":
+            model = ref.unidefense.UniDefenseModelRes18(drop_rate=0.0)
+            R, N = 96, 4
+        else:
+            model = ref.unidefense.UniDefenseModelRes50(drop_rate=0.0)
+            R, N = 64, 4
+        P.fill_state_dict_(model, salt=5)
+        model.train()
+        x = T(f"full_x_{arch}", (N, 3, R, R))
+        if eps:
+            x = x + eps * torch.randn(x.shape, generator=torch.Generator().manual_seed(1))
+        labels = torch.tensor([0] * (N // 2) + [1] * (N // 2))
+        orig_dropout = F.dropout
+        F.dropout = lambda t, p=0.5, training=True, inplace=False: t * 1.0
+        try:
+            out = model(x)
+        finally:
+            F.dropout = orig_dropout
+        ld = out["loss_dict"]
+        nr = N // 2
+        tri = ref.loss.LOSSES["aw_triplet"]
+        ce = torch.nn.CrossEntropyLoss()
+        tri_loss = sum(tri(f, labels) for f in ld["triplet"])
+        loss = (ce(out["cls_out"], labels) + 0.1 * ld["freq_mask"].mean() + 0.1 * ld["spat_mask"].mean()
+                + 0.1 * tri_loss + 0.1 * ld["spatial"][:nr].mean() + 1.0 * ld["freq"][:nr].mean())
+        named = [(n_, p_) for n_, p_ in model.named_parameters() if p_.requires_grad]
+        gs = torch.autograd.grad(loss, [p_ for _, p_ in named], allow_unused=True)
+        pg = {}
+        for (n_, p_), g in zip(named, gs):
+            if g is None:
+                pg[n_] = None
+                continue
+            idx = P.sample_indices(p_.numel(), 16, n_)
+            pg[n_] = {"norm": g.norm().item(), "sample": g.flatten()[idx].clone()}
+        sd_after = model.state_dict()
+        bn_after = {k: v.clone() for k, v in sd_after.items() if k.endswith("running_mean")
+                    and k.startswith(("bottleneck", "freq_filter", "spat_filter"))}
+        return {"arch": arch, "R": R, "N": N, "labels": labels, "cls_out": out["cls_out"].detach(),
+                "rec_sample": out["rec"].detach()[:, :, ::7, ::5].clone(), "spatial": ld["spatial"].detach(),
+                "freq": ld["freq"].detach(), "freq_mask": ld["freq_mask"].detach(),
+                "spat_mask": ld["spat_mask"].detach(), "factorization": ld["factorization"].detach(),
+                "triplet_feats": [t.detach() for t in ld["triplet"]], "loss": loss.detach(), "param_grads": pg,
+                "bn_after": bn_after, "state_dict_shapes": {k: tuple(v.shape) for k, v in sd_after.items()}}
+
+    fix, alt = run(0.0), run(2e-7)
+    noise = {}
+    for k in ("cls_out", "rec_sample", "spatial", "freq", "freq_mask", "spat_mask", "factorization", "loss"):
+        noise[k] = float((fix[k] - alt[k]).abs().max())
+    noise["triplet_feats"] = [float((a - b).abs().max()) for a, b in zip(fix["triplet_feats"], alt["triplet_feats"])]
+    noise["bn_after"] = {k: float((fix["bn_after"][k] - alt["bn_after"][k]).abs().max()) for k in fix["bn_after"]}
+    noise["grad_norm_rel"] = {k: abs(v["norm"] - alt["param_grads"][k]["norm"]) / (v["norm"] + 1e-30)
+                              for k, v in fix["param_grads"].items() if v is not None}
+    fix["noise"] = noise
+    return fix
 
 
 def main():
