@@ -137,3 +137,75 @@ const float2* ud_twiddles(int n) {
   g_tw_cache[key] = d;
   return d;
 }
+
+static std::map<std::pair<int, std::pair<int, int>>, float2*> g_lerp_cache;
+
+const float2* ud_lerp_table(int in, int out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    ud_set_error("cudaGetDevice failed");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(g_tw_mutex);
+  auto key = std::make_pair(dev, std::make_pair(in, out));
+  auto it = g_lerp_cache.find(key);
+  if (it != g_lerp_cache.end()) return it->second;
+  std::vector<float2> h((size_t)out);
+  const float scale = ud_ac_scale(in, out);
+  for (int d = 0; d < out; ++d) {
+    const float src = scale * (float)d;       // ATen: area_pixel_compute_source_index, align_corners=True
+    const int i0 = (int)src;
+    union { int i; float f; } u;
+    u.i = i0;
+    h[d] = make_float2(u.f, src - (float)i0);
+  }
+  float2* p = nullptr;
+  if (cudaMalloc(&p, sizeof(float2) * (size_t)out) != cudaSuccess) {
+    ud_set_error("cudaMalloc(lerp table %d->%d) failed", in, out);
+    return nullptr;
+  }
+  if (cudaMemcpy(p, h.data(), sizeof(float2) * (size_t)out, cudaMemcpyHostToDevice) != cudaSuccess) {
+    ud_set_error("cudaMemcpy(lerp table %d->%d) failed", in, out);
+    cudaFree(p);
+    return nullptr;
+  }
+  g_lerp_cache[key] = p;
+  return p;
+}
+
+static std::map<std::pair<int, std::pair<int, int>>, int2*> g_range_cache;
+
+const int2* ud_lerp_ranges(int in, int out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    ud_set_error("cudaGetDevice failed");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(g_tw_mutex);
+  auto key = std::make_pair(dev, std::make_pair(in, out));
+  auto it = g_range_cache.find(key);
+  if (it != g_range_cache.end()) return it->second;
+  std::vector<int2> h((size_t)in, make_int2(out, -1));
+  const float scale = ud_ac_scale(in, out);
+  for (int d = 0; d < out; ++d) {
+    const float src = scale * (float)d;
+    const int i0 = (int)src;
+    const int i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+    for (int i : {i0, i1}) {
+      if (d < h[i].x) h[i].x = d;
+      if (d > h[i].y) h[i].y = d;
+    }
+  }
+  int2* p = nullptr;
+  if (cudaMalloc(&p, sizeof(int2) * (size_t)in) != cudaSuccess) {
+    ud_set_error("cudaMalloc(lerp ranges %d->%d) failed", in, out);
+    return nullptr;
+  }
+  if (cudaMemcpy(p, h.data(), sizeof(int2) * (size_t)in, cudaMemcpyHostToDevice) != cudaSuccess) {
+    ud_set_error("cudaMemcpy(lerp ranges %d->%d) failed", in, out);
+    cudaFree(p);
+    return nullptr;
+  }
+  g_range_cache[key] = p;
+  return p;
+}

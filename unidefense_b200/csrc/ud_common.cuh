@@ -69,6 +69,20 @@ __device__ __forceinline__ float ud_block_sum(float v, float* red) {
 __device__ __forceinline__ float ud_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float ud_sign(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
+// cp.async (LDGSTS): global -> shared without staging in registers, so a CTA can put its whole tile in
+// flight before it starts computing.  4- and 8-byte forms (cache at all levels), 16-byte form bypasses L1.
+__device__ __forceinline__ void ud_cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void ud_cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void ud_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void ud_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void ud_cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // activation codes shared with the host API
 #define UD_ACT_NONE 0
 #define UD_ACT_RELU 1

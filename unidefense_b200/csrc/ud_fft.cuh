@@ -109,6 +109,7 @@ struct UdStaticStages<N, NS, R0, Rest...> {
 
 template <int N, int... Rs>
 struct UdStaticPlan {
+  static constexpr bool kInPlace = false;
   static constexpr int kN = N;
   __device__ __forceinline__ int n() const { return N; }
   // Runs all stages; data must be in `a` and visible (caller synced).  Returns the buffer
@@ -119,6 +120,7 @@ struct UdStaticPlan {
 };
 
 struct UdDynPlan {
+  static constexpr bool kInPlace = false;
   int n_;
   int nstages;
   int radix[UD_FFT_MAX_STAGES];
@@ -149,6 +151,80 @@ struct UdDynPlan {
   }
 };
 
+// ---- in-place static plans ------------------------------------------------------------------
+// Same Stockham stages, but ONE buffer: every thread first pulls all of its butterflies for the stage
+// into registers, the CTA synchronises, then results are written back in autosort order.  Halves the
+// shared memory per CTA (=> twice the resident CTAs per SM) at the price of one extra barrier per
+// stage.  N, L (lines per CTA) and THREADS are compile-time so every index is constant-folded.
+template <int R, int N, int NS, int L, int THREADS>
+__device__ __forceinline__ void ud_fft_stage_ip(float2* __restrict__ buf, const float2* __restrict__ tw) {
+  constexpr int T = N / R;
+  constexpr int TOTAL = L * T;
+  constexpr int PASSES = (TOTAL + THREADS - 1) / THREADS;
+  constexpr int LS = N | 1;
+  constexpr int TS = T / NS;
+  constexpr bool FULL = (PASSES * THREADS == TOTAL);
+  float2 v[PASSES][R];
+#pragma unroll
+  for (int p = 0; p < PASSES; ++p) {
+    const int wi = (int)threadIdx.x + p * THREADS;
+    if (FULL || wi < TOTAL) {
+      const int line = wi / T;
+      const int j = wi - line * T;
+      const float2* src = buf + line * LS + j;
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[p][r] = src[r * T];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < PASSES; ++p) {
+    const int wi = (int)threadIdx.x + p * THREADS;
+    if (FULL || wi < TOTAL) {
+      const int line = wi / T;
+      const int j = wi - line * T;
+      const int q = j / NS;
+      const int k = j - q * NS;
+      if (NS > 1) {
+        const int t1 = k * TS;
+#pragma unroll
+        for (int r = 1; r < R; ++r) v[p][r] = ud_cmul(v[p][r], tw[r * t1]);
+      }
+      UdBfly<R>::run(v[p]);
+      float2* dst = buf + line * LS + q * (NS * R) + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) dst[r * NS] = v[p][r];
+    }
+  }
+  __syncthreads();
+}
+
+template <int N, int NS, int L, int THREADS, int... Rs>
+struct UdIpStages;
+template <int N, int NS, int L, int THREADS>
+struct UdIpStages<N, NS, L, THREADS> {
+  static __device__ __forceinline__ void run(float2*, const float2*) {}
+};
+template <int N, int NS, int L, int THREADS, int R0, int... Rest>
+struct UdIpStages<N, NS, L, THREADS, R0, Rest...> {
+  static __device__ __forceinline__ void run(float2* buf, const float2* tw) {
+    ud_fft_stage_ip<R0, N, NS, L, THREADS>(buf, tw);
+    UdIpStages<N, NS * R0, L, THREADS, Rest...>::run(buf, tw);
+  }
+};
+
+// Plan concept used by the kernels:  kInPlace, n(), run(a, b, tw, L, LS) -> buffer holding the result.
+template <int N, int L, int THREADS, int... Rs>
+struct UdStaticPlanIP {
+  static constexpr bool kInPlace = true;
+  static constexpr int kN = N;
+  __device__ __forceinline__ int n() const { return N; }
+  __device__ __forceinline__ float2* run(float2* a, float2*, const float2* tw, int, int) const {
+    UdIpStages<N, 1, L, THREADS, Rs...>::run(a, tw);
+    return a;
+  }
+};
+
 typedef UdStaticPlan<380, 19, 5, 4> UdPlan380;
 typedef UdStaticPlan<256, 4, 4, 4, 4> UdPlan256;
 typedef UdStaticPlan<224, 7, 4, 4, 2> UdPlan224;
@@ -161,5 +237,12 @@ bool ud_make_dyn_plan(int n, UdDynPlan* plan);
 // Device twiddle table exp(-2 pi i t/n), t in [0,n), cached per (device, n) for the process
 // lifetime (mutex-guarded, never freed).  nullptr on failure (error set).
 const float2* ud_twiddles(int n);
+// align_corners=True bilinear table for resizing `in` -> `out` samples along one axis:
+// entry d = { __int_as_float(i0), l1 } with ATen's fp32 arithmetic (scale=(in-1)/(out-1), src=scale*d,
+// i0=(int)src, l1=src-i0); i1 = i0 + (i0 < in-1), l0 = 1-l1.  Cached per (device, in, out) like the twiddles.
+const float2* ud_lerp_table(int in, int out);
+// For the transposed resize: entry j (0 <= j < in) = {first, last} output sample whose taps (i0 or i1)
+// include input sample j; first > last when none does.  Derived from the same fp32 table.
+const int2* ud_lerp_ranges(int in, int out);
 // padded line stride (odd) for n-point lines
 static inline int ud_line_stride(int n) { return n | 1; }

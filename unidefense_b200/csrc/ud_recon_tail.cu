@@ -20,81 +20,139 @@
 #include "../../include/unidefense_b200.h"
 #include "ud_fft.cuh"
 
-#define RT_THREADS 256
-#define RT_LINES 12   // row pairs per CTA (rows kernels) / columns per CTA (cols kernels)
+#define RT_ROW_T 256   // threads of the rows kernels
+#define RT_ROW_L 12    // row PAIRS (complex lines) per CTA of the rows kernels  -> 24 image rows
+#define RT_COL_T 320   // threads of the cols kernels
+#define RT_COL_L 16    // columns per CTA of the cols kernels (16 float2 = one 128-byte line per row)
+#define RT_HSTAGE 12   // rows_bwd: max horizontal-transpose items per thread kept in registers
+#define RT_VGRP 3      // row pairs whose vertical lerps are staged per barrier (RT_ROW_L % RT_VGRP == 0)
 
-static inline int rt_whp(int W) { return ((W / 2 + 1) + 3) & ~3; }  // padded half width (float2)
+static inline int rt_whp(int W) { return ((W / 2 + 1) + 15) & ~15; }  // padded half width (float2)
+
+__device__ __forceinline__ void rt_tab(const float2 t, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  i0 = __float_as_int(t.x);
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = t.y;
+  l0 = 1.f - l1;
+}
+
+// Vertical lerp of the two image rows (ra, ra+1) of a pair into vA/vB [w] (shared memory).
+__device__ __forceinline__ void rt_vrows(const float* __restrict__ decp, const float2* __restrict__ ytab_g, int ra, int h,
+                                         int w, int H, float* __restrict__ vA, float* __restrict__ vB) {
+  if (ra >= H) return;
+  int a0, a1, b0, b1;
+  float la0, la1, lb0, lb1;
+  rt_tab(__ldg(ytab_g + ra), h, a0, a1, la0, la1);
+  const bool has_b = ra + 1 < H;
+  rt_tab(__ldg(ytab_g + (has_b ? ra + 1 : ra)), h, b0, b1, lb0, lb1);
+  const float* pa0 = decp + (long long)a0 * w;
+  const float* pa1 = decp + (long long)a1 * w;
+  const float* pb0 = decp + (long long)b0 * w;
+  const float* pb1 = decp + (long long)b1 * w;
+  for (int c = threadIdx.x; c < w; c += blockDim.x) {
+    vA[c] = la0 * __ldg(pa0 + c) + la1 * __ldg(pa1 + c);
+    vB[c] = has_b ? (lb0 * __ldg(pb0 + c) + lb1 * __ldg(pb1 + c)) : 0.f;
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // forward rows: grid (row_tiles, planes_in_chunk)
+//   shared: tw[n] | xtab[n] | buf0[L*LS] (| buf1[L*LS] when the plan ping-pongs) | vbuf[2][2][w]
 // ------------------------------------------------------------------------------------------
 template <class Plan>
-__global__ void __launch_bounds__(RT_THREADS)
+__global__ void __launch_bounds__(RT_ROW_T)
 rt_rows_fwd_kernel(Plan plan, const float* __restrict__ dec, const float* __restrict__ x,
                    float* __restrict__ rec, float2* __restrict__ Y, float* __restrict__ part_spatial,
-                   const float2* __restrict__ tw_g, int plane0, int h, int w, int H, int W, float sy, float sx,
-                   int row_tiles) {
+                   const float2* __restrict__ tw_g, const float2* __restrict__ ytab_g,
+                   const float2* __restrict__ xtab_g, int plane0, int h, int w, int H, int W, int row_tiles) {
   extern __shared__ float2 smem[];
   const int n = plan.n();  // == W
   const int LS = n | 1;
   float2* tw = smem;
-  float2* buf0 = tw + n;
-  float2* buf1 = buf0 + RT_LINES * LS;
+  float2* xtab = tw + n;
+  float2* buf0 = xtab + n;
+  float2* buf1 = Plan::kInPlace ? buf0 : buf0 + RT_ROW_L * LS;
+  float* vbuf = reinterpret_cast<float*>(buf1 + RT_ROW_L * LS);
   __shared__ float red[33];
 
   const int tile = blockIdx.x;
   const int pl = blockIdx.y;             // plane within chunk
   const long long plane = plane0 + pl;   // global (n*C + c)
-  const int r0 = tile * (2 * RT_LINES);
-  const int Wh = W / 2 + 1;
-  const int WhP = ((Wh + 3) & ~3);
+  const int r0 = tile * (2 * RT_ROW_L);
+  W = n;                                 // W == n: lets static plans constant-fold every index below
+  const int Wh = n / 2 + 1;
+  const int WhP = (Wh + 15) & ~15;
 
-  for (int t = threadIdx.x; t < n; t += blockDim.x) tw[t] = tw_g[t];
-
+  for (int t = threadIdx.x; t < n; t += RT_ROW_T) {
+    tw[t] = __ldg(tw_g + t);
+    xtab[t] = __ldg(xtab_g + t);
+  }
   const float* decp = dec + plane * (long long)h * w;
   const float* xp = x + plane * (long long)H * W;
   float* recp = rec + plane * (long long)H * W;
 
-  float acc = 0.f;
-  for (int p = 0; p < RT_LINES; ++p) {
-    const int ra = r0 + 2 * p, rb = ra + 1;
+  // whole x tile in flight first: x[ra][c] -> line[p][c].x, x[ra+1][c] -> .y (overwritten in place by d below)
+  for (int p = 0; p < RT_ROW_L; ++p) {
+    const int ra = r0 + 2 * p;
+    if (ra >= H) break;
+    const float* xa_p = xp + (long long)ra * W;
     float2* line = buf0 + p * LS;
-    if (ra >= H) {
-      for (int c = threadIdx.x; c < W; c += blockDim.x) line[c] = make_float2(0.f, 0.f);
-      continue;
-    }
-    const UdLerp ya = ud_lerp_ac(ra, h, sy);
-    const bool has_b = rb < H;
-    const UdLerp yb = ud_lerp_ac(has_b ? rb : ra, h, sy);
-    const float* da0 = decp + ya.i0 * w;
-    const float* da1 = decp + ya.i1 * w;
-    const float* db0 = decp + yb.i0 * w;
-    const float* db1 = decp + yb.i1 * w;
-    for (int c = threadIdx.x; c < W; c += blockDim.x) {
-      const UdLerp xc = ud_lerp_ac(c, w, sx);
-      const float va = ya.l0 * (xc.l0 * __ldg(da0 + xc.i0) + xc.l1 * __ldg(da0 + xc.i1)) +
-                       ya.l1 * (xc.l0 * __ldg(da1 + xc.i0) + xc.l1 * __ldg(da1 + xc.i1));
-      const float xa = __ldg(xp + (long long)ra * W + c);
-      recp[(long long)ra * W + c] = va;
-      const float dA = va - xa;
-      float dB = 0.f;
-      if (has_b) {
-        const float vb = yb.l0 * (xc.l0 * __ldg(db0 + xc.i0) + xc.l1 * __ldg(db0 + xc.i1)) +
-                         yb.l1 * (xc.l0 * __ldg(db1 + xc.i0) + xc.l1 * __ldg(db1 + xc.i1));
-        const float xb = __ldg(xp + (long long)rb * W + c);
-        recp[(long long)rb * W + c] = vb;
-        dB = vb - xb;
-      }
-      acc += fabsf(dA) + fabsf(dB);
-      line[c] = make_float2(dA, dB);
+    const bool has_b = ra + 1 < H;
+    for (int c = threadIdx.x; c < W; c += RT_ROW_T) {
+      ud_cp_async4(&line[c].x, xa_p + c);
+      if (has_b) ud_cp_async4(&line[c].y, xa_p + W + c);
     }
   }
+  ud_cp_async_commit();
+  for (int q = 0; q < RT_VGRP; ++q) rt_vrows(decp, ytab_g, r0 + 2 * q, h, w, H, vbuf + 2 * q * w, vbuf + (2 * q + 1) * w);
+  ud_cp_async_wait_all();
   __syncthreads();
-  float2* res = plan.run(buf0, buf1, tw, RT_LINES, LS);
+  float acc = 0.f;
+  for (int g = 0; g < RT_ROW_L / RT_VGRP; ++g) {
+    if (g + 1 < RT_ROW_L / RT_VGRP) {
+      float* nv = vbuf + ((g + 1) & 1) * (2 * RT_VGRP) * w;
+      for (int q = 0; q < RT_VGRP; ++q)
+        rt_vrows(decp, ytab_g, r0 + 2 * ((g + 1) * RT_VGRP + q), h, w, H, nv + 2 * q * w, nv + (2 * q + 1) * w);
+    }
+    const float* vg = vbuf + (g & 1) * (2 * RT_VGRP) * w;
+#pragma unroll
+    for (int q = 0; q < RT_VGRP; ++q) {
+      const int p = g * RT_VGRP + q;
+      const int ra = r0 + 2 * p;
+      const float* vA = vg + 2 * q * w;
+      const float* vB = vA + w;
+      float2* line = buf0 + p * LS;
+      if (ra >= H) {
+        for (int c = threadIdx.x; c < W; c += RT_ROW_T) line[c] = make_float2(0.f, 0.f);
+      } else {
+        const bool has_b = ra + 1 < H;
+        float* ra_p = recp + (long long)ra * W;
+        for (int c = threadIdx.x; c < W; c += RT_ROW_T) {
+          int i0, i1;
+          float l0, l1;
+          rt_tab(xtab[c], w, i0, i1, l0, l1);
+          const float2 xv = line[c];
+          const float va = l0 * vA[i0] + l1 * vA[i1];
+          __stcs(ra_p + c, va);
+          const float dA = va - xv.x;
+          float dB = 0.f;
+          if (has_b) {
+            const float vb = l0 * vB[i0] + l1 * vB[i1];
+            __stcs(ra_p + W + c, vb);
+            dB = vb - xv.y;
+          }
+          acc += fabsf(dA) + fabsf(dB);
+          line[c] = make_float2(dA, dB);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float2* res = plan.run(buf0, buf1, tw, RT_ROW_L, LS);
 
   // unpack the two real rows of each pair: A[k] = (Z[k]+conj Z[n-k])/2, B[k] = (Z[k]-conj Z[n-k])/(2i)
   float2* Yp = Y + (long long)pl * H * WhP;
-  for (int t = threadIdx.x; t < RT_LINES * Wh; t += blockDim.x) {
+  for (int t = threadIdx.x; t < RT_ROW_L * Wh; t += RT_ROW_T) {
     const int p = t / Wh, k = t - p * Wh;
     const int ra = r0 + 2 * p;
     if (ra >= H) continue;
@@ -111,7 +169,7 @@ rt_rows_fwd_kernel(Plan plan, const float* __restrict__ dec, const float* __rest
 // forward cols: grid (col_tiles, planes_in_chunk).  Column FFT length n = H.
 // ------------------------------------------------------------------------------------------
 template <class Plan>
-__global__ void __launch_bounds__(RT_THREADS)
+__global__ void __launch_bounds__(RT_COL_T)
 rt_cols_fwd_kernel(Plan plan, const float2* __restrict__ Y, float* __restrict__ part_freq,
                    uint8_t* __restrict__ signs, const float2* __restrict__ tw_g, int plane0, int H, int W,
                    int col_tiles) {
@@ -120,30 +178,32 @@ rt_cols_fwd_kernel(Plan plan, const float2* __restrict__ Y, float* __restrict__ 
   const int LS = n | 1;
   float2* tw = smem;
   float2* buf0 = tw + n;
-  float2* buf1 = buf0 + RT_LINES * LS;
+  float2* buf1 = Plan::kInPlace ? buf0 : buf0 + RT_COL_L * LS;
   __shared__ float red[33];
 
   const int tile = blockIdx.x;
   const int pl = blockIdx.y;
   const long long plane = plane0 + pl;
+  H = n;                                 // H == n: constant-folds the index math for static plans
   const int Wh = W / 2 + 1;
-  const int WhP = ((Wh + 3) & ~3);
-  const int k0 = tile * RT_LINES;
-  const int ncols = min(RT_LINES, Wh - k0);
+  const int WhP = (Wh + 15) & ~15;
+  const int k0 = tile * RT_COL_L;
+  const int ncols = min(RT_COL_L, Wh - k0);
 
-  for (int t = threadIdx.x; t < n; t += blockDim.x) tw[t] = tw_g[t];
+  for (int t = threadIdx.x; t < n; t += RT_COL_T) tw[t] = __ldg(tw_g + t);
   const float2* Yp = Y + (long long)pl * H * WhP;
-  for (int t = threadIdx.x; t < H * RT_LINES; t += blockDim.x) {
-    const int r = t / RT_LINES, cc = t - r * RT_LINES;
-    float2 v = make_float2(0.f, 0.f);
-    if (cc < ncols) v = Yp[(long long)r * WhP + k0 + cc];
-    buf0[cc * LS + r] = v;
+  for (int t = threadIdx.x; t < H * RT_COL_L; t += RT_COL_T) {
+    const int r = t / RT_COL_L, cc = t - r * RT_COL_L;
+    if (cc < ncols) ud_cp_async8(&buf0[cc * LS + r], Yp + (long long)r * WhP + k0 + cc);
+    else buf0[cc * LS + r] = make_float2(0.f, 0.f);
   }
+  ud_cp_async_commit();
+  ud_cp_async_wait_all();
   __syncthreads();
-  float2* res = plan.run(buf0, buf1, tw, RT_LINES, LS);
+  float2* res = plan.run(buf0, buf1, tw, RT_COL_L, LS);
 
   float acc = 0.f;
-  for (int t = threadIdx.x; t < ncols * H; t += blockDim.x) {
+  for (int t = threadIdx.x; t < ncols * H; t += RT_COL_T) {
     const int cc = t / H, j = t - cc * H;
     const float2 v = res[cc * LS + j];
     acc += fabsf(v.x) + fabsf(v.y);
@@ -181,7 +241,7 @@ __global__ void rt_finalize_kernel(const float* __restrict__ part_spatial, const
 // inverse via the swap trick: IFFT(z) = swap(FFT(swap(z))).
 // ------------------------------------------------------------------------------------------
 template <class Plan>
-__global__ void __launch_bounds__(RT_THREADS)
+__global__ void __launch_bounds__(RT_COL_T)
 rt_cols_bwd_kernel(Plan plan, const uint8_t* __restrict__ signs, const float* __restrict__ g_freq,
                    float2* __restrict__ T, const float2* __restrict__ tw_g, int plane0, int C, int H, int W,
                    float gscale) {
@@ -190,7 +250,7 @@ rt_cols_bwd_kernel(Plan plan, const uint8_t* __restrict__ signs, const float* __
   const int LS = n | 1;
   float2* tw = smem;
   float2* buf0 = tw + n;
-  float2* buf1 = buf0 + RT_LINES * LS;
+  float2* buf1 = Plan::kInPlace ? buf0 : buf0 + RT_COL_L * LS;
 
   const int tile = blockIdx.x;
   const int pl = blockIdx.y;
@@ -198,13 +258,14 @@ rt_cols_bwd_kernel(Plan plan, const uint8_t* __restrict__ signs, const float* __
   const int smp = (int)(plane / C);
   if (g_freq[smp] == 0.f) return;  // whole plane contributes nothing; the rows kernel skips its FFT too
   const float gf = g_freq[smp] * gscale;
+  H = n;
   const int Wh = W / 2 + 1;
-  const int WhP = ((Wh + 3) & ~3);
-  const int k0 = tile * RT_LINES;
-  const int ncols = min(RT_LINES, Wh - k0);
+  const int WhP = (Wh + 15) & ~15;
+  const int k0 = tile * RT_COL_L;
+  const int ncols = min(RT_COL_L, Wh - k0);
 
-  for (int t = threadIdx.x; t < n; t += blockDim.x) tw[t] = tw_g[t];
-  for (int t = threadIdx.x; t < RT_LINES * H; t += blockDim.x) {
+  for (int t = threadIdx.x; t < n; t += RT_COL_T) tw[t] = __ldg(tw_g + t);
+  for (int t = threadIdx.x; t < RT_COL_L * H; t += RT_COL_T) {
     const int cc = t / H, j = t - cc * H;
     float2 v = make_float2(0.f, 0.f);
     if (cc < ncols) {
@@ -216,10 +277,10 @@ rt_cols_bwd_kernel(Plan plan, const uint8_t* __restrict__ signs, const float* __
     buf0[cc * LS + j] = v;
   }
   __syncthreads();
-  float2* res = plan.run(buf0, buf1, tw, RT_LINES, LS);
+  float2* res = plan.run(buf0, buf1, tw, RT_COL_L, LS);
   float2* Tp = T + (long long)pl * H * WhP;
-  for (int t = threadIdx.x; t < H * RT_LINES; t += blockDim.x) {
-    const int r = t / RT_LINES, cc = t - r * RT_LINES;
+  for (int t = threadIdx.x; t < H * RT_COL_L; t += RT_COL_T) {
+    const int r = t / RT_COL_L, cc = t - r * RT_COL_L;
     if (cc < ncols) {
       const float2 v = res[cc * LS + r];
       Tp[(long long)r * WhP + k0 + cc] = make_float2(v.y, v.x);  // swap back
@@ -232,21 +293,28 @@ rt_cols_bwd_kernel(Plan plan, const uint8_t* __restrict__ signs, const float* __
 // g_rec[r,c] = gs*sign(d[r,c]) + Re sum_{k<Wh} T[r,k] e^{+2 pi i k c / W}; then the transposed
 // bilinear resize accumulates into g_dec (pre-zeroed).  Two rows are packed per complex line by
 // folding T into its Hermitian part Th (Re IFFT(T) == IFFT(Th)) and transforming Th_a + i Th_b.
+//   shared: tw[n] | xtab[n] | buf0[L*LS] (| buf1) | vbuf[2][2][w]
+// After the FFT a line holds (g_b[c], g_a[c]) per column.  The transposed resize runs horizontally
+// first (gather through xtab, both rows of a pair at once, results staged in registers and written back
+// over the line), then vertically: one thread per dec column walks the tile's rows in order carrying two
+// running sums (rows i and i+1) and flushes each finished dec row with one atomicAdd.
 // ------------------------------------------------------------------------------------------
 template <class Plan>
-__global__ void __launch_bounds__(RT_THREADS)
+__global__ void __launch_bounds__(RT_ROW_T)
 rt_rows_bwd_kernel(Plan plan, const float* __restrict__ dec, const float* __restrict__ x,
                    const float2* __restrict__ T, const float* __restrict__ g_spatial,
                    const float* __restrict__ g_freq, float* __restrict__ g_dec,
-                   const float2* __restrict__ tw_g, int plane0, int C, int h, int w, int H, int W, float sy,
-                   float sx, float sp_scale) {
+                   const float2* __restrict__ tw_g, const float2* __restrict__ ytab_g,
+                   const float2* __restrict__ xtab_g, const int2* __restrict__ jtab_g, int plane0, int C, int h,
+                   int w, int H, int W, float sp_scale) {
   extern __shared__ float2 smem[];
   const int n = plan.n();  // == W
   const int LS = n | 1;
   float2* tw = smem;
-  float2* buf0 = tw + n;
-  float2* buf1 = buf0 + RT_LINES * LS;
-  float* hrow = reinterpret_cast<float*>(buf1 + RT_LINES * LS);  // [2*RT_LINES][w]
+  float2* xtab = tw + n;
+  float2* buf0 = xtab + n;
+  float2* buf1 = Plan::kInPlace ? buf0 : buf0 + RT_ROW_L * LS;
+  float* vbuf = reinterpret_cast<float*>(buf1 + RT_ROW_L * LS);
 
   const int tile = blockIdx.x;
   const int pl = blockIdx.y;
@@ -255,17 +323,78 @@ rt_rows_bwd_kernel(Plan plan, const float* __restrict__ dec, const float* __rest
   const float gs = g_spatial[smp] * sp_scale;
   const bool has_f = g_freq[smp] != 0.f;
   if (gs == 0.f && !has_f) return;
-  const int r0 = tile * (2 * RT_LINES);
-  const int Wh = W / 2 + 1;
-  const int WhP = ((Wh + 3) & ~3);
-  const int nrows = min(2 * RT_LINES, H - r0);
+  const int r0 = tile * (2 * RT_ROW_L);
+  W = n;
+  const int Wh = n / 2 + 1;
+  const int WhP = (Wh + 15) & ~15;
+  const int nrows = min(2 * RT_ROW_L, H - r0);
+
+  for (int t = threadIdx.x; t < n; t += RT_ROW_T) {
+    tw[t] = __ldg(tw_g + t);
+    xtab[t] = __ldg(xtab_g + t);
+  }
+  // sign(rec - x) of the tile first (2+2 bits per row pair and column), while the buffer is still free:
+  // x is prefetched into the lines with cp.async exactly like the forward does.
+  uint8_t* sgn = reinterpret_cast<uint8_t*>(vbuf + 4 * RT_VGRP * w);   // [RT_ROW_L][n]
+  if (gs != 0.f) {
+    const float* decp = dec + plane * (long long)h * w;
+    const float* xp = x + plane * (long long)H * W;
+    for (int p = 0; p < RT_ROW_L; ++p) {
+      const int ra = r0 + 2 * p;
+      if (ra >= H) break;
+      const float* xa_p = xp + (long long)ra * W;
+      float2* line = buf0 + p * LS;
+      const bool has_b = ra + 1 < H;
+      for (int c = threadIdx.x; c < W; c += RT_ROW_T) {
+        ud_cp_async4(&line[c].x, xa_p + c);
+        if (has_b) ud_cp_async4(&line[c].y, xa_p + W + c);
+      }
+    }
+    ud_cp_async_commit();
+    for (int q = 0; q < RT_VGRP; ++q) rt_vrows(decp, ytab_g, r0 + 2 * q, h, w, H, vbuf + 2 * q * w, vbuf + (2 * q + 1) * w);
+    ud_cp_async_wait_all();
+    __syncthreads();
+    for (int g = 0; g < RT_ROW_L / RT_VGRP; ++g) {
+      if (g + 1 < RT_ROW_L / RT_VGRP) {
+        float* nv = vbuf + ((g + 1) & 1) * (2 * RT_VGRP) * w;
+        for (int q = 0; q < RT_VGRP; ++q)
+          rt_vrows(decp, ytab_g, r0 + 2 * ((g + 1) * RT_VGRP + q), h, w, H, nv + 2 * q * w, nv + (2 * q + 1) * w);
+      }
+      const float* vg = vbuf + (g & 1) * (2 * RT_VGRP) * w;
+#pragma unroll
+      for (int q = 0; q < RT_VGRP; ++q) {
+        const int p = g * RT_VGRP + q;
+        const int ra = r0 + 2 * p;
+        const float* vA = vg + 2 * q * w;
+        const float* vB = vA + w;
+        const float2* line = buf0 + p * LS;
+        const bool live = ra < H, has_b = ra + 1 < H;
+        for (int c = threadIdx.x; c < W; c += RT_ROW_T) {
+          uint8_t code = 0;
+          if (live) {
+            int i0, i1;
+            float l0, l1;
+            rt_tab(xtab[c], w, i0, i1, l0, l1);
+            const float2 xv = line[c];
+            const float dA = (l0 * vA[i0] + l1 * vA[i1]) - xv.x;
+            code = dA > 0.f ? 1 : (dA < 0.f ? 2 : 0);
+            if (has_b) {
+              const float dB = (l0 * vB[i0] + l1 * vB[i1]) - xv.y;
+              code |= dB > 0.f ? 4 : (dB < 0.f ? 8 : 0);
+            }
+          }
+          sgn[p * n + c] = code;
+        }
+      }
+      __syncthreads();
+    }
+  }
 
   float2* res = buf0;
   if (has_f) {
-    for (int t = threadIdx.x; t < n; t += blockDim.x) tw[t] = tw_g[t];
     const float2* Tp = T + (long long)pl * H * WhP;
     // build V = Th_a + i Th_b (swapped for the inverse) for k in [0, Wh) and its mirror n-k
-    for (int t = threadIdx.x; t < RT_LINES * Wh; t += blockDim.x) {
+    for (int t = threadIdx.x; t < RT_ROW_L * Wh; t += RT_ROW_T) {
       const int p = t / Wh, k = t - p * Wh;
       const int ra = r0 + 2 * p;
       float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
@@ -284,85 +413,129 @@ rt_rows_bwd_kernel(Plan plan, const float* __restrict__ dec, const float* __rest
       }
     }
     __syncthreads();
-    res = plan.run(buf0, buf1, tw, RT_LINES, LS);
-    // res[p][c] (swapped back) = (g_a[c], g_b[c])  ->  read as (.y, .x)
+    res = plan.run(buf0, buf1, tw, RT_ROW_L, LS);   // res[p][c] = (g_b[c], g_a[c])
+  } else {
+    for (int t = threadIdx.x; t < RT_ROW_L * LS; t += RT_ROW_T) buf0[t] = make_float2(0.f, 0.f);
+    __syncthreads();
+  }
+  if (gs != 0.f) {  // g += gs * sign(rec - x)
+    for (int t = threadIdx.x; t < RT_ROW_L * n; t += RT_ROW_T) {
+      const int p = t / n, c = t - p * n;
+      const uint8_t code = sgn[t];
+      float2 g = res[p * LS + c];
+      g.y += (code & 1) ? gs : ((code & 2) ? -gs : 0.f);
+      g.x += (code & 4) ? gs : ((code & 8) ? -gs : 0.f);
+      res[p * LS + c] = g;
+    }
+    __syncthreads();
   }
 
-  // pass 1: per output row, g = gs*sign(d) + g_fft ; horizontal transposed lerp by gather
-  const float* decp = dec + plane * (long long)h * w;
-  const float* xp = x + plane * (long long)H * W;
-  // write g rows into the free ping-pong buffer as plain floats [row][W]
-  float* grow = reinterpret_cast<float*>(res == buf0 ? buf1 : buf0);
-  for (int t = threadIdx.x; t < nrows * W; t += blockDim.x) {
-    const int rr = t / W, c = t - rr * W;
-    const int r = r0 + rr;
-    float g = 0.f;
-    if (has_f) {
-      const float2 v = res[(rr >> 1) * LS + c];
-      g = (rr & 1) ? v.x : v.y;
-    }
-    if (gs != 0.f) {
-      const UdLerp yr = ud_lerp_ac(r, h, sy);
-      const UdLerp xc = ud_lerp_ac(c, w, sx);
-      const float* d0 = decp + yr.i0 * w;
-      const float* d1 = decp + yr.i1 * w;
-      const float v = yr.l0 * (xc.l0 * __ldg(d0 + xc.i0) + xc.l1 * __ldg(d0 + xc.i1)) +
-                      yr.l1 * (xc.l0 * __ldg(d1 + xc.i0) + xc.l1 * __ldg(d1 + xc.i1));
-      g += gs * ud_sign(v - __ldg(xp + (long long)r * W + c));
-    }
-    grow[rr * W + c] = g;
-  }
-  __syncthreads();
-  const float inv_sx = sx > 0.f ? 1.f / sx : 0.f;
-  for (int t = threadIdx.x; t < nrows * w; t += blockDim.x) {
-    const int rr = t / w, j = t - rr * w;
-    int c_lo, c_hi;
-    if (sx > 0.f) {
-      c_lo = max(0, (int)floorf((float)(j - 1) * inv_sx) - 1);
-      c_hi = min(W - 1, (int)ceilf((float)(j + 1) * inv_sx) + 1);
-    } else {
-      c_lo = 0;
-      c_hi = W - 1;
-    }
-    float a = 0.f;
-    for (int c = c_lo; c <= c_hi; ++c) {
-      const UdLerp xc = ud_lerp_ac(c, w, sx);
-      float wgt = 0.f;
-      if (xc.i0 == j) wgt += xc.l0;
-      if (xc.i1 == j) wgt += xc.l1;
-      a = fmaf(wgt, grow[rr * W + c], a);
-    }
-    hrow[rr * w + j] = a;
-  }
-  __syncthreads();
-  // pass 2: vertical transposed lerp; this tile's rows touch dec rows [i_lo, i_hi]
-  const int i_lo = ud_lerp_ac(r0, h, sy).i0;
-  const int i_hi = ud_lerp_ac(r0 + nrows - 1, h, sy).i1;
   float* gd = g_dec + plane * (long long)h * w;
-  for (int t = threadIdx.x; t < (i_hi - i_lo + 1) * w; t += blockDim.x) {
-    const int ii = t / w, j = t - ii * w;
-    const int i = i_lo + ii;
-    float a = 0.f;
-    for (int rr = 0; rr < nrows; ++rr) {
-      const UdLerp yr = ud_lerp_ac(r0 + rr, h, sy);
-      float wgt = 0.f;
-      if (yr.i0 == i) wgt += yr.l0;
-      if (yr.i1 == i) wgt += yr.l1;
-      if (wgt != 0.f) a = fmaf(wgt, hrow[rr * w + j], a);
+  const int items = RT_ROW_L * w;
+  if (items <= RT_HSTAGE * RT_ROW_T && w <= n) {   // staged results are written back over the line (n slots)
+    // horizontal transposed lerp, both rows of a pair per item, staged in registers.  jtab[j] = first/last
+    // output column whose two taps include dec column j (exact, from the same fp32 table as the forward).
+    float2 hv[RT_HSTAGE];
+    int p = 0, j = threadIdx.x;
+    while (j >= w) { j -= w; ++p; }
+#pragma unroll
+    for (int s = 0; s < RT_HSTAGE; ++s) {
+      hv[s] = make_float2(0.f, 0.f);
+      if (p < RT_ROW_L) {
+        const int2 cr = __ldg(jtab_g + j);
+        const float2* line = res + p * LS;
+        float ax = 0.f, ay = 0.f;
+        for (int c = cr.x; c <= cr.y; ++c) {
+          const float2 t = xtab[c];
+          const int i0 = __float_as_int(t.x);
+          const float wgt = (i0 == j) ? (1.f - t.y) + ((i0 == w - 1) ? t.y : 0.f) : t.y;   // i0 == j-1 -> the l1 tap
+          const float2 g = line[c];
+          ax = fmaf(wgt, g.x, ax);
+          ay = fmaf(wgt, g.y, ay);
+        }
+        hv[s] = make_float2(ax, ay);
+      }
+      j += RT_ROW_T;
+      while (j >= w) { j -= w; ++p; }
     }
-    if (a != 0.f) atomicAdd(gd + (long long)i * w + j, a);
+    __syncthreads();
+    p = 0;
+    j = threadIdx.x;
+    while (j >= w) { j -= w; ++p; }
+#pragma unroll
+    for (int s = 0; s < RT_HSTAGE; ++s) {
+      if (p < RT_ROW_L) res[p * LS + j] = hv[s];
+      j += RT_ROW_T;
+      while (j >= w) { j -= w; ++p; }
+    }
+    __syncthreads();
+    // vertical transposed lerp: thread j walks the rows of the tile
+    for (int j = threadIdx.x; j < w; j += RT_ROW_T) {
+      int cur = __float_as_int(__ldg(ytab_g + r0).x);
+      float acc0 = 0.f, acc1 = 0.f;
+      for (int rr = 0; rr < nrows; ++rr) {
+        int i0, i1;
+        float l0, l1;
+        rt_tab(__ldg(ytab_g + r0 + rr), h, i0, i1, l0, l1);
+        while (cur < i0) {
+          if (acc0 != 0.f) atomicAdd(gd + (long long)cur * w + j, acc0);
+          acc0 = acc1;
+          acc1 = 0.f;
+          ++cur;
+        }
+        const float2 g2 = res[(rr >> 1) * LS + j];
+        const float v = (rr & 1) ? g2.x : g2.y;
+        acc0 = fmaf(l0, v, acc0);
+        if (i1 > i0) acc1 = fmaf(l1, v, acc1);
+        else acc0 = fmaf(l1, v, acc0);
+      }
+      if (acc0 != 0.f) atomicAdd(gd + (long long)cur * w + j, acc0);
+      if (acc1 != 0.f && cur + 1 < h) atomicAdd(gd + (long long)(cur + 1) * w + j, acc1);
+    }
+  } else {
+    // wide decoder planes: no register staging; distribute each horizontal result with two atomics
+    for (int it = threadIdx.x; it < nrows * w; it += RT_ROW_T) {
+      const int rr = it / w, j = it - rr * w;
+      const int2 cr = __ldg(jtab_g + j);
+      const float2* line = res + (rr >> 1) * LS;
+      float a = 0.f;
+      for (int c = cr.x; c <= cr.y; ++c) {
+        int i0, i1;
+        float l0, l1;
+        rt_tab(xtab[c], w, i0, i1, l0, l1);
+        const float wgt = ((i0 == j) ? l0 : 0.f) + ((i1 == j) ? l1 : 0.f);
+        const float2 g = line[c];
+        a = fmaf(wgt, (rr & 1) ? g.x : g.y, a);
+      }
+      int i0, i1;
+      float l0, l1;
+      rt_tab(__ldg(ytab_g + r0 + rr), h, i0, i1, l0, l1);
+      if (a != 0.f) {
+        atomicAdd(gd + (long long)i0 * w + j, l0 * a);
+        if (l1 != 0.f) atomicAdd(gd + (long long)i1 * w + j, l1 * a);
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static size_t rt_fft_smem(int n) { return sizeof(float2) * ((size_t)n + 2ull * RT_LINES * (n | 1)); }
+static bool rt_static_size(int n) { return n == 380 || n == 256 || n == 224 || n == 299; }
+static size_t rt_rows_smem(int n, int w) {
+  const size_t bufs = rt_static_size(n) ? 1 : 2;
+  return sizeof(float2) * (2ull * n + bufs * RT_ROW_L * (size_t)(n | 1)) + sizeof(float) * 4ull * RT_VGRP * w +
+         (size_t)RT_ROW_L * n;   // + sign bytes of the tile (rows_bwd)
+}
+static size_t rt_cols_smem(int n) {
+  const size_t bufs = rt_static_size(n) ? 1 : 2;
+  return sizeof(float2) * ((size_t)n + bufs * RT_COL_L * (size_t)(n | 1));
+}
 
 static int rt_chunk_samples(int N, int C, int H, int W) {
-  // keep the Y/T workspace (plus the streamed images) comfortably inside the 126 MB L2
+  // the Y/T workspace of a chunk must stay L2-resident (126 MB) next to the streamed images
   const size_t per_sample = (size_t)C * H * rt_whp(W) * sizeof(float2);
-  int chunk = (int)((24ull << 20) / (per_sample ? per_sample : 1));
+  int chunk = (int)((64ull << 20) / (per_sample ? per_sample : 1));
   if (chunk < 1) chunk = 1;
   if (chunk > N) chunk = N;
   return chunk;
@@ -371,7 +544,7 @@ static int rt_chunk_samples(int N, int C, int H, int W) {
 extern "C" size_t ud_recon_tail_workspace_bytes(int N, int C, int h, int w, int H, int W) {
   (void)h; (void)w;
   const int chunk = rt_chunk_samples(N, C, H, W);
-  const int row_tiles = ud_cdiv(H, 2 * RT_LINES), col_tiles = ud_cdiv(W / 2 + 1, RT_LINES);
+  const int row_tiles = ud_cdiv(H, 2 * RT_ROW_L), col_tiles = ud_cdiv(W / 2 + 1, RT_COL_L);
   size_t y = ud_align_up((size_t)chunk * C * H * rt_whp(W) * sizeof(float2), 256);
   size_t ps = ud_align_up((size_t)N * C * row_tiles * sizeof(float), 256);
   size_t pf = ud_align_up((size_t)N * C * col_tiles * sizeof(float), 256);
@@ -382,18 +555,22 @@ extern "C" size_t ud_recon_tail_signs_bytes(int N, int C, int H, int W) {
   return (size_t)N * C * (W / 2 + 1) * H;
 }
 
-// Runs the body with PLANVAR bound to the static plan for n when one exists, else a dynamic plan.
-#define RT_DISPATCH_PLAN(n, PLANVAR, ...)                                          \
-  do {                                                                             \
-    if ((n) == 380) { UdPlan380 PLANVAR; __VA_ARGS__; }                            \
-    else if ((n) == 256) { UdPlan256 PLANVAR; __VA_ARGS__; }                       \
-    else if ((n) == 224) { UdPlan224 PLANVAR; __VA_ARGS__; }                       \
-    else if ((n) == 299) { UdPlan299 PLANVAR; __VA_ARGS__; }                       \
-    else { UdDynPlan PLANVAR; ud_make_dyn_plan((n), &PLANVAR); __VA_ARGS__; }      \
+// Runs the body with PLANVAR bound to the in-place static plan for n when one exists, else a dynamic plan.
+#define RT_DISPATCH_PLAN(n, L, THREADS, PLANVAR, ...)                                                    \
+  do {                                                                                                   \
+    if ((n) == 380) { UdStaticPlanIP<380, L, THREADS, 19, 5, 4> PLANVAR; __VA_ARGS__; }                  \
+    else if ((n) == 256) { UdStaticPlanIP<256, L, THREADS, 4, 4, 4, 4> PLANVAR; __VA_ARGS__; }           \
+    else if ((n) == 224) { UdStaticPlanIP<224, L, THREADS, 7, 4, 4, 2> PLANVAR; __VA_ARGS__; }           \
+    else if ((n) == 299) { UdStaticPlanIP<299, L, THREADS, 23, 13> PLANVAR; __VA_ARGS__; }               \
+    else { UdDynPlan PLANVAR; ud_make_dyn_plan((n), &PLANVAR); __VA_ARGS__; }                            \
   } while (0)
 
 template <class K>
 static int rt_set_smem(K kernel, size_t bytes) {
+  if (bytes > (227u << 10)) {
+    ud_set_error("recon_tail: needs %zu bytes of shared memory per CTA (> 227 KB)", bytes);
+    return UD_ERR_UNSUPPORTED;
+  }
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) {
     ud_set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", bytes, cudaGetErrorString(e));
@@ -407,6 +584,7 @@ static int rt_validate(int N, int C, int h, int w, int H, int W) {
              "recon_tail: bad shape N=%d C=%d h=%d w=%d H=%d W=%d", N, C, h, w, H, W);
   UD_REQUIRE(ud_fft_size_supported(H) && ud_fft_size_supported(W), UD_ERR_UNSUPPORTED,
              "recon_tail: FFT size %dx%d unsupported (prime factors must be <= 23, n <= %d)", H, W, UD_FFT_MAX_N);
+  UD_REQUIRE((long long)N * C <= 65535LL * 64, UD_ERR_UNSUPPORTED, "recon_tail: too many planes");
   return UD_OK;
 }
 
@@ -420,36 +598,37 @@ extern "C" int ud_recon_tail_fwd(const float* dec, const float* x, float* rec, f
   UD_REQUIRE(ws_bytes >= ud_recon_tail_workspace_bytes(N, C, h, w, H, W), UD_ERR_WORKSPACE,
              "recon_tail_fwd: workspace too small (%zu < %zu)", ws_bytes,
              ud_recon_tail_workspace_bytes(N, C, h, w, H, W));
-  const int chunk = rt_chunk_samples(N, C, H, W);
+  int chunk = rt_chunk_samples(N, C, H, W);
+  if (chunk * C > 65535) chunk = 65535 / C;
   const int Wh = W / 2 + 1;
-  const int row_tiles = ud_cdiv(H, 2 * RT_LINES), col_tiles = ud_cdiv(Wh, RT_LINES);
+  const int row_tiles = ud_cdiv(H, 2 * RT_ROW_L), col_tiles = ud_cdiv(Wh, RT_COL_L);
   char* p = static_cast<char*>(ws);
   float2* Y = reinterpret_cast<float2*>(p);
-  p += ud_align_up((size_t)chunk * C * H * rt_whp(W) * sizeof(float2), 256);
+  p += ud_align_up((size_t)rt_chunk_samples(N, C, H, W) * C * H * rt_whp(W) * sizeof(float2), 256);
   float* part_sp = reinterpret_cast<float*>(p);
   p += ud_align_up((size_t)N * C * row_tiles * sizeof(float), 256);
   float* part_fr = reinterpret_cast<float*>(p);
   const float2* twW = ud_twiddles(W);
   const float2* twH = ud_twiddles(H);
-  if (!twW || !twH) return UD_ERR_CUDA;
-  const float sy = ud_ac_scale(h, H), sx = ud_ac_scale(w, W);
-  const size_t smW = rt_fft_smem(W), smH = rt_fft_smem(H);
+  const float2* ytab = ud_lerp_table(h, H);
+  const float2* xtab = ud_lerp_table(w, W);
+  if (!twW || !twH || !ytab || !xtab) return UD_ERR_CUDA;
+  const size_t smW = rt_rows_smem(W, w), smH = rt_cols_smem(H);
 
   for (int s0 = 0; s0 < N; s0 += chunk) {
     const int ns = (N - s0 < chunk) ? (N - s0) : chunk;
     const int planes = ns * C, plane0 = s0 * C;
-    RT_DISPATCH_PLAN(W, plan, {
+    RT_DISPATCH_PLAN(W, RT_ROW_L, RT_ROW_T, plan, {
       auto k = rt_rows_fwd_kernel<decltype(plan)>;
       if ((rc = rt_set_smem(k, smW)) != UD_OK) return rc;
-      k<<<dim3(row_tiles, planes), RT_THREADS, smW, stream>>>(plan, dec, x, rec, Y, part_sp, twW, plane0, h, w, H,
-                                                               W, sy, sx, row_tiles);
+      k<<<dim3(row_tiles, planes), RT_ROW_T, smW, stream>>>(plan, dec, x, rec, Y, part_sp, twW, ytab, xtab, plane0,
+                                                             h, w, H, W, row_tiles);
     });
     if ((rc = ud_check_launch("rt_rows_fwd")) != UD_OK) return rc;
-    RT_DISPATCH_PLAN(H, plan, {
+    RT_DISPATCH_PLAN(H, RT_COL_L, RT_COL_T, plan, {
       auto k = rt_cols_fwd_kernel<decltype(plan)>;
       if ((rc = rt_set_smem(k, smH)) != UD_OK) return rc;
-      k<<<dim3(col_tiles, planes), RT_THREADS, smH, stream>>>(plan, Y, part_fr, signs, twH, plane0, H, W,
-                                                               col_tiles);
+      k<<<dim3(col_tiles, planes), RT_COL_T, smH, stream>>>(plan, Y, part_fr, signs, twH, plane0, H, W, col_tiles);
     });
     if ((rc = ud_check_launch("rt_cols_fwd")) != UD_OK) return rc;
   }
@@ -469,16 +648,19 @@ extern "C" int ud_recon_tail_bwd(const float* dec, const float* x, const uint8_t
              "recon_tail_bwd: null pointer");
   UD_REQUIRE(ws_bytes >= ud_recon_tail_workspace_bytes(N, C, h, w, H, W), UD_ERR_WORKSPACE,
              "recon_tail_bwd: workspace too small");
-  const int chunk = rt_chunk_samples(N, C, H, W);
+  int chunk = rt_chunk_samples(N, C, H, W);
+  if (chunk * C > 65535) chunk = 65535 / C;
   const int Wh = W / 2 + 1;
-  const int row_tiles = ud_cdiv(H, 2 * RT_LINES), col_tiles = ud_cdiv(Wh, RT_LINES);
+  const int row_tiles = ud_cdiv(H, 2 * RT_ROW_L), col_tiles = ud_cdiv(Wh, RT_COL_L);
   float2* T = reinterpret_cast<float2*>(ws);
   const float2* twW = ud_twiddles(W);
   const float2* twH = ud_twiddles(H);
-  if (!twW || !twH) return UD_ERR_CUDA;
-  const float sy = ud_ac_scale(h, H), sx = ud_ac_scale(w, W);
-  const size_t smH = rt_fft_smem(H);
-  const size_t smW = rt_fft_smem(W) + sizeof(float) * 2ull * RT_LINES * w;
+  const float2* ytab = ud_lerp_table(h, H);
+  const float2* xtab = ud_lerp_table(w, W);
+  if (!twW || !twH || !ytab || !xtab) return UD_ERR_CUDA;
+  const int2* jtab = ud_lerp_ranges(w, W);
+  if (!jtab) return UD_ERR_CUDA;
+  const size_t smH = rt_cols_smem(H), smW = rt_rows_smem(W, w);
   // freq[n] = nrm/(C*H*Wh) * sum |D'| with D' the unnormalised spectrum, so the sign spectrum
   // carries nrm/(C*H*Wh) and the adjoint of the unnormalised forward is the unnormalised inverse.
   const float nrm = norm_ortho ? 1.f / sqrtf((float)H * (float)W) : 1.f;
@@ -488,17 +670,17 @@ extern "C" int ud_recon_tail_bwd(const float* dec, const float* x, const uint8_t
   for (int s0 = 0; s0 < N; s0 += chunk) {
     const int ns = (N - s0 < chunk) ? (N - s0) : chunk;
     const int planes = ns * C, plane0 = s0 * C;
-    RT_DISPATCH_PLAN(H, plan, {
+    RT_DISPATCH_PLAN(H, RT_COL_L, RT_COL_T, plan, {
       auto k = rt_cols_bwd_kernel<decltype(plan)>;
       if ((rc = rt_set_smem(k, smH)) != UD_OK) return rc;
-      k<<<dim3(col_tiles, planes), RT_THREADS, smH, stream>>>(plan, signs, g_freq, T, twH, plane0, C, H, W, gscale);
+      k<<<dim3(col_tiles, planes), RT_COL_T, smH, stream>>>(plan, signs, g_freq, T, twH, plane0, C, H, W, gscale);
     });
     if ((rc = ud_check_launch("rt_cols_bwd")) != UD_OK) return rc;
-    RT_DISPATCH_PLAN(W, plan, {
+    RT_DISPATCH_PLAN(W, RT_ROW_L, RT_ROW_T, plan, {
       auto k = rt_rows_bwd_kernel<decltype(plan)>;
       if ((rc = rt_set_smem(k, smW)) != UD_OK) return rc;
-      k<<<dim3(row_tiles, planes), RT_THREADS, smW, stream>>>(plan, dec, x, T, g_spatial, g_freq, g_dec, twW,
-                                                               plane0, C, h, w, H, W, sy, sx, sp_scale);
+      k<<<dim3(row_tiles, planes), RT_ROW_T, smW, stream>>>(plan, dec, x, T, g_spatial, g_freq, g_dec, twW, ytab,
+                                                             xtab, jtab, plane0, C, h, w, H, W, sp_scale);
     });
     if ((rc = ud_check_launch("rt_rows_bwd")) != UD_OK) return rc;
   }
