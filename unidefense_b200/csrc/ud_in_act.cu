@@ -25,142 +25,262 @@
 namespace cg = cooperative_groups;
 
 #define IA_THREADS 256
+#define IA_WARPS (IA_THREADS / 32)
 #define IA_VMAX_FWD 9
 #define IA_VMAX_BWD 5
+#define IA_MAX_CS 8
 
-// cluster-wide (or block-wide when CS==1) sum, broadcast to all threads of all CTAs.
-// `slot` is a per-CTA shared float written by thread 0; `red` is block scratch (33 floats).
-template <bool CLUSTER>
-__device__ __forceinline__ float ia_group_sum(float v, float* red, float* slot, int cs) {
-  float t = ud_block_sum(v, red);
-  if (CLUSTER) {
-    cg::cluster_group cluster = cg::this_cluster();
-    if (threadIdx.x == 0) *slot = t;
-    cluster.sync();
-    float tot = 0.f;
-    for (int r = 0; r < cs; ++r) tot += *cluster.map_shared_rank(slot, r);  // fixed order: deterministic
-    t = tot;
+template <int ACT>
+__device__ __forceinline__ float ia_sigmoid(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+template <int ACT>
+__device__ __forceinline__ float ia_act(float z) {
+  if (ACT == UD_ACT_RELU) return fmaxf(z, 0.f);
+  if (ACT == UD_ACT_SWISH) return z * ia_sigmoid<ACT>(z);
+  return z;
+}
+// d act(z)/dz; swish: s*(1+z*(1-s))  (SwishImplementation.backward, model/efficientnet/utils.py:73-77)
+template <int ACT>
+__device__ __forceinline__ float ia_act_grad(float z) {
+  if (ACT == UD_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (ACT == UD_ACT_SWISH) {
+    const float s = ia_sigmoid<ACT>(z);
+    return s * fmaf(z, 1.f - s, 1.f);
   }
-  return t;
+  return 1.f;
 }
 
+// Chan et al. merge of (count, mean, M2) partial statistics: exact two-pass quality without a second
+// group-wide reduction.
+struct IaStat {
+  float n, mean, m2;
+};
+__device__ __forceinline__ IaStat ia_merge(IaStat a, IaStat b) {
+  const float n = a.n + b.n;
+  if (n == 0.f) return a;
+  const float d = b.mean - a.mean;
+  const float f = __fdividef(b.n, n);
+  IaStat r;
+  r.n = n;
+  r.mean = fmaf(d, f, a.mean);
+  r.m2 = a.m2 + b.m2 + d * d * a.n * f;
+  return r;
+}
+__device__ __forceinline__ IaStat ia_warp_merge(IaStat s) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    IaStat t;
+    t.n = __shfl_xor_sync(0xffffffffu, s.n, o);
+    t.mean = __shfl_xor_sync(0xffffffffu, s.mean, o);
+    t.m2 = __shfl_xor_sync(0xffffffffu, s.m2, o);
+    // order the pair by lane so that both partners compute bit-identical results
+    s = ((threadIdx.x & o) == 0) ? ia_merge(s, t) : ia_merge(t, s);
+  }
+  return s;
+}
+
+// Work decomposition: a plane is split over `nw` WARPS, each owning a contiguous slab of ceil(E4/nw)
+// float4 that it keeps in registers (lane-strided, 512 contiguous bytes per warp access).
+//   nw <= 8  : G = nw warps per plane, 8/G planes per 256-thread CTA (no cluster) -- small planes still put
+//              ~150 KB per SM in flight;
+//   nw  > 8  : a thread-block cluster of cs = nw/8 CTAs per plane.
+// Reductions: per-warp shuffles, then ONE exchange: each warp publishes its partial to a shared-memory slot
+// (for clusters: PUSHED into the slot array of every CTA of the cluster through DSMEM), one barrier, and
+// every thread folds the slots of its plane in fixed order (deterministic, no trailing barrier).
+struct IaGeom {
+  int plane, wsub, nw, slot0, rank;
+  bool live;
+};
 template <bool CLUSTER>
-__global__ void __launch_bounds__(IA_THREADS)
+__device__ __forceinline__ IaGeom ia_geom(int planes, int G, int cs) {
+  IaGeom g;
+  const int warp = threadIdx.x >> 5;
+  if (CLUSTER) {
+    g.plane = blockIdx.x / cs;
+    g.rank = blockIdx.x % cs;
+    g.wsub = g.rank * IA_WARPS + warp;
+    g.nw = cs * IA_WARPS;
+    g.slot0 = 0;
+  } else {
+    g.plane = blockIdx.x * (IA_WARPS / G) + warp / G;
+    g.rank = 0;
+    g.wsub = warp % G;
+    g.nw = G;
+    g.slot0 = (warp / G) * G;
+  }
+  g.live = g.plane < planes;
+  return g;
+}
+
+template <bool CLUSTER, int K>
+__device__ __forceinline__ void ia_exchange(float (*slots)[K], const float (&mine)[K], int rank, int cs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (CLUSTER) {
+    cg::cluster_group cluster = cg::this_cluster();
+    if (lane < cs) {
+      float(*remote)[K] = cluster.map_shared_rank(slots, lane);
+#pragma unroll
+      for (int k = 0; k < K; ++k) remote[rank * IA_WARPS + warp][k] = mine[k];
+    }
+    cluster.sync();
+  } else {
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) slots[warp][k] = mine[k];
+    }
+    __syncthreads();
+  }
+}
+
+template <bool CLUSTER, int ACT>
+__global__ void __launch_bounds__(IA_THREADS, 4)
 ia_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               float4* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-              float* __restrict__ ymean_out, int C, int E4, int cs, int vpt, float eps, int act) {
-  __shared__ float red[33];
-  __shared__ float slots[3];
-  const int plane = CLUSTER ? (blockIdx.x / cs) : blockIdx.x;
-  const int rank = CLUSTER ? (blockIdx.x % cs) : 0;
-  const int per_cta = (E4 + cs - 1) / cs;
-  const int beg = rank * per_cta;
-  const int end = min(E4, beg + per_cta);
-  const float4* xp = x + (long long)plane * E4;
+              float* __restrict__ ymean_out, int planes, int C, int E4, int G, int cs, int vpt, float eps) {
+  __shared__ float slots[IA_MAX_CS * IA_WARPS][3];
+  __shared__ float yslots[IA_MAX_CS * IA_WARPS][1];
+  const IaGeom ge = ia_geom<CLUSTER>(planes, G, cs);
+  const int lane = threadIdx.x & 31;
+  const int per_w = (E4 + ge.nw - 1) / ge.nw;
+  const int beg = ge.wsub * per_w;
+  const int end = ge.live ? min(E4, beg + per_w) : 0;
+  const float4* xp = x + (long long)ge.plane * E4;
   float4 v[IA_VMAX_FWD];
   float s = 0.f;
+  int cnt = 0;
 #pragma unroll
   for (int i = 0; i < IA_VMAX_FWD; ++i) {
-    const int idx = beg + i * IA_THREADS + threadIdx.x;
+    const int idx = beg + i * 32 + lane;
     if (i < vpt && idx < end) {
       v[i] = __ldcs(xp + idx);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      cnt += 4;
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  const float invE = 1.f / (4.f * (float)E4);
-  const float mu = ia_group_sum<CLUSTER>(s, red, &slots[0], cs) * invE;
+#pragma unroll
+  for (int i = 0; i < IA_VMAX_FWD; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  // thread-local two-pass statistics, then one merge tree
+  IaStat st;
+  st.n = (float)cnt;
+  st.mean = cnt ? s / (float)cnt : 0.f;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < IA_VMAX_FWD; ++i) {
-    const int idx = beg + i * IA_THREADS + threadIdx.x;
+    const int idx = beg + i * 32 + lane;
     if (i < vpt && idx < end) {
-      const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+      const float a = v[i].x - st.mean, b = v[i].y - st.mean, c = v[i].z - st.mean, d = v[i].w - st.mean;
       q += (a * a + b * b) + (c * c + d * d);
     }
   }
-  const float var = ia_group_sum<CLUSTER>(q, red, &slots[1], cs) * invE;
-  const float rstd = rsqrtf(var + eps);
-  const int ch = plane % C;
+  st.m2 = q;
+  st = ia_warp_merge(st);
+  const float mine[3] = {st.n, st.mean, st.m2};
+  ia_exchange<CLUSTER, 3>(slots, mine, ge.rank, cs);
+  IaStat tot = {slots[ge.slot0][0], slots[ge.slot0][1], slots[ge.slot0][2]};
+  for (int i = 1; i < ge.nw; ++i)
+    tot = ia_merge(tot, IaStat{slots[ge.slot0 + i][0], slots[ge.slot0 + i][1], slots[ge.slot0 + i][2]});
+  const float mu = tot.mean;
+  const float rstd = rsqrtf(tot.m2 / fmaxf(tot.n, 1.f) + eps);
+  const int ch = ge.live ? ge.plane % C : 0;
   const float g = gamma ? __ldg(gamma + ch) : 1.f;
   const float b = beta ? __ldg(beta + ch) : 0.f;
   const float a_ = g * rstd, b_ = b - mu * g * rstd;
-  float4* yp = y + (long long)plane * E4;
+  float4* yp = y + (long long)ge.plane * E4;
   float ys = 0.f;
 #pragma unroll
   for (int i = 0; i < IA_VMAX_FWD; ++i) {
-    const int idx = beg + i * IA_THREADS + threadIdx.x;
+    const int idx = beg + i * 32 + lane;
     if (i < vpt && idx < end) {
       float4 o;
-      o.x = ud_act_fwd(fmaf(v[i].x, a_, b_), act);
-      o.y = ud_act_fwd(fmaf(v[i].y, a_, b_), act);
-      o.z = ud_act_fwd(fmaf(v[i].z, a_, b_), act);
-      o.w = ud_act_fwd(fmaf(v[i].w, a_, b_), act);
+      o.x = ia_act<ACT>(fmaf(v[i].x, a_, b_));
+      o.y = ia_act<ACT>(fmaf(v[i].y, a_, b_));
+      o.z = ia_act<ACT>(fmaf(v[i].z, a_, b_));
+      o.w = ia_act<ACT>(fmaf(v[i].w, a_, b_));
       ys += (o.x + o.y) + (o.z + o.w);
       yp[idx] = o;
     }
   }
-  if (ymean_out != nullptr) {
-    const float t = ia_group_sum<CLUSTER>(ys, red, &slots[2], cs) * invE;
-    if (rank == 0 && threadIdx.x == 0) ymean_out[plane] = t;
+  const bool writer = ge.live && ge.wsub == 0 && lane == 0;
+  if (writer) {
+    mean_out[ge.plane] = mu;
+    rstd_out[ge.plane] = rstd;
   }
-  if (rank == 0 && threadIdx.x == 0) {
-    mean_out[plane] = mu;
-    rstd_out[plane] = rstd;
+  if (ymean_out != nullptr) {   // uniform across the grid
+    ys = ud_warp_sum(ys);
+    const float ymine[1] = {ys};
+    ia_exchange<CLUSTER, 1>(yslots, ymine, ge.rank, cs);
+    if (writer) {
+      float t = 0.f;
+      for (int i = 0; i < ge.nw; ++i) t += yslots[ge.slot0 + i][0];
+      ymean_out[ge.plane] = t / tot.n;
+    }
   }
-  if (CLUSTER) cg::this_cluster().sync();  // keep our smem alive until every peer has read it
 }
 
-template <bool CLUSTER>
-__global__ void __launch_bounds__(IA_THREADS)
+template <bool CLUSTER, int ACT>
+__global__ void __launch_bounds__(IA_THREADS, 4)
 ia_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const float* __restrict__ gamma,
               const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd_in,
               const float* __restrict__ g_ymean, float4* __restrict__ gx, float* __restrict__ s1_out,
-              float* __restrict__ s2_out, int C, int E4, int cs, int vpt, int act) {
-  __shared__ float red[33];
-  __shared__ float slots[2];
-  const int plane = CLUSTER ? (blockIdx.x / cs) : blockIdx.x;
-  const int rank = CLUSTER ? (blockIdx.x % cs) : 0;
-  const int per_cta = (E4 + cs - 1) / cs;
-  const int beg = rank * per_cta;
-  const int end = min(E4, beg + per_cta);
-  const long long base = (long long)plane * E4;
-  const int ch = plane % C;
+              float* __restrict__ s2_out, int planes, int C, int E4, int G, int cs, int vpt) {
+  __shared__ float slots[IA_MAX_CS * IA_WARPS][2];
+  const IaGeom ge = ia_geom<CLUSTER>(planes, G, cs);
+  const int lane = threadIdx.x & 31;
+  const int per_w = (E4 + ge.nw - 1) / ge.nw;
+  const int beg = ge.wsub * per_w;
+  const int end = ge.live ? min(E4, beg + per_w) : 0;
+  const int pl = ge.live ? ge.plane : 0;
+  const long long base = (long long)pl * E4;
+  const int ch = pl % C;
   const float g = gamma ? __ldg(gamma + ch) : 1.f;
   const float b = beta ? __ldg(beta + ch) : 0.f;
-  const float mu = mean[plane], rstd = rstd_in[plane];
+  const float mu = mean[pl], rstd = rstd_in[pl];
   const float invE = 1.f / (4.f * (float)E4);
-  const float gadd = g_ymean ? g_ymean[plane] * invE : 0.f;  // d mean(y) term
+  const float gadd = g_ymean ? g_ymean[pl] * invE : 0.f;  // d mean(y) term
   float4 xh[IA_VMAX_BWD], gz[IA_VMAX_BWD];
-  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < IA_VMAX_BWD; ++i) {
-    const int idx = beg + i * IA_THREADS + threadIdx.x;
+  for (int i = 0; i < IA_VMAX_BWD; ++i) {   // all loads in flight before any math
+    const int idx = beg + i * 32 + lane;
     if (i < vpt && idx < end) {
-      const float4 xv = __ldcs(x + base + idx);
-      const float4 gv = __ldcs(gy + base + idx);
-      float4 h, z;
-      h.x = (xv.x - mu) * rstd; h.y = (xv.y - mu) * rstd; h.z = (xv.z - mu) * rstd; h.w = (xv.w - mu) * rstd;
-      z.x = (gv.x + gadd) * ud_act_grad(fmaf(h.x, g, b), act);
-      z.y = (gv.y + gadd) * ud_act_grad(fmaf(h.y, g, b), act);
-      z.z = (gv.z + gadd) * ud_act_grad(fmaf(h.z, g, b), act);
-      z.w = (gv.w + gadd) * ud_act_grad(fmaf(h.w, g, b), act);
-      s1 += (z.x + z.y) + (z.z + z.w);
-      s2 += (z.x * h.x + z.y * h.y) + (z.z * h.z + z.w * h.w);
-      xh[i] = h;
-      gz[i] = z;
+      xh[i] = __ldcs(x + base + idx);
+      gz[i] = __ldcs(gy + base + idx);
     } else {
       xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  const float S1 = ia_group_sum<CLUSTER>(s1, red, &slots[0], cs);
-  const float S2 = ia_group_sum<CLUSTER>(s2, red, &slots[1], cs);
+  float s1 = 0.f, s2 = 0.f;
+  const float nmr = -mu * rstd;
+#pragma unroll
+  for (int i = 0; i < IA_VMAX_BWD; ++i) {
+    const int idx = beg + i * 32 + lane;
+    if (i < vpt && idx < end) {
+      float4 h, z;
+      h.x = fmaf(xh[i].x, rstd, nmr); h.y = fmaf(xh[i].y, rstd, nmr);
+      h.z = fmaf(xh[i].z, rstd, nmr); h.w = fmaf(xh[i].w, rstd, nmr);
+      z.x = (gz[i].x + gadd) * ia_act_grad<ACT>(fmaf(h.x, g, b));
+      z.y = (gz[i].y + gadd) * ia_act_grad<ACT>(fmaf(h.y, g, b));
+      z.z = (gz[i].z + gadd) * ia_act_grad<ACT>(fmaf(h.z, g, b));
+      z.w = (gz[i].w + gadd) * ia_act_grad<ACT>(fmaf(h.w, g, b));
+      s1 += (z.x + z.y) + (z.z + z.w);
+      s2 += (z.x * h.x + z.y * h.y) + (z.z * h.z + z.w * h.w);
+      xh[i] = h;
+      gz[i] = z;
+    }
+  }
+  s1 = ud_warp_sum(s1);
+  s2 = ud_warp_sum(s2);
+  const float mine[2] = {s1, s2};
+  ia_exchange<CLUSTER, 2>(slots, mine, ge.rank, cs);
+  float S1 = 0.f, S2 = 0.f;
+  for (int i = 0; i < ge.nw; ++i) {
+    S1 += slots[ge.slot0 + i][0];
+    S2 += slots[ge.slot0 + i][1];
+  }
   const float m1 = S1 * invE, m2 = S2 * invE, k = g * rstd;
 #pragma unroll
   for (int i = 0; i < IA_VMAX_BWD; ++i) {
-    const int idx = beg + i * IA_THREADS + threadIdx.x;
+    const int idx = beg + i * 32 + lane;
     if (i < vpt && idx < end) {
       float4 o;
       o.x = k * (gz[i].x - m1 - xh[i].x * m2);
@@ -170,11 +290,10 @@ ia_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const
       gx[base + idx] = o;
     }
   }
-  if (rank == 0 && threadIdx.x == 0) {
-    s1_out[plane] = S1;
-    s2_out[plane] = S2;
+  if (ge.live && ge.wsub == 0 && lane == 0) {
+    s1_out[ge.plane] = S1;
+    s2_out[ge.plane] = S2;
   }
-  if (CLUSTER) cg::this_cluster().sync();
 }
 
 // ---- generic fallback: any plane size (odd E, huge planes): one CTA per plane, re-reads hit L1/L2 ----
@@ -261,20 +380,30 @@ __global__ void ia_param_grad_kernel(const float* __restrict__ s1, const float* 
   if (gbeta) gbeta[c] = b;
 }
 
-static bool ia_pick(int E, int vmax, int* cs, int* vpt) {
+// smallest power-of-two warp count nw (<= 64) whose per-warp slab fits vmax float4 per lane
+static bool ia_pick(int E, int vmax, int* G, int* cs, int* vpt) {
   if (E % 4 != 0) return false;
   const int E4 = E / 4;
-  for (int c = 1; c <= 8; c *= 2) {
-    const int per = (E4 + c - 1) / c;
-    const int v = (per + IA_THREADS - 1) / IA_THREADS;
+  for (int nw = 1; nw <= IA_MAX_CS * IA_WARPS; nw *= 2) {
+    const int per = (E4 + nw - 1) / nw;
+    const int v = (per + 31) / 32;
     if (v <= vmax) {
-      *cs = c;
+      *G = nw <= IA_WARPS ? nw : IA_WARPS;
+      *cs = nw <= IA_WARPS ? 1 : nw / IA_WARPS;
       *vpt = v;
       return true;
     }
   }
   return false;
 }
+
+// expands STMT once per activation code with ACT_ bound to the compile-time constant
+#define IA_ACT_SWITCH(act, STMT)                                            \
+  do {                                                                      \
+    if ((act) == UD_ACT_SWISH) { constexpr int ACT_ = UD_ACT_SWISH; STMT; } \
+    else if ((act) == UD_ACT_RELU) { constexpr int ACT_ = UD_ACT_RELU; STMT; } \
+    else { constexpr int ACT_ = UD_ACT_NONE; STMT; }                        \
+  } while (0)
 
 template <class K, class... Args>
 static int ia_launch(K kernel, int blocks, int cs, cudaStream_t stream, Args... args) {
@@ -309,14 +438,15 @@ extern "C" int ud_in_act_fwd(const float* x, const float* gamma, const float* be
   const int planes = N * C;
   int cs = 1, vpt = 1;
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
-  if (aligned && ia_pick(HW, IA_VMAX_FWD, &cs, &vpt)) {
+  int G = 1;
+  if (aligned && ia_pick(HW, IA_VMAX_FWD, &G, &cs, &vpt)) {
     const float4* x4 = reinterpret_cast<const float4*>(x);
     float4* y4 = reinterpret_cast<float4*>(y);
     if (cs == 1)
-      return ia_launch(ia_fwd_kernel<false>, planes, 1, stream, x4, gamma, beta, y4, mean, rstd, ymean, C, HW / 4,
-                       cs, vpt, eps, act);
-    return ia_launch(ia_fwd_kernel<true>, planes * cs, cs, stream, x4, gamma, beta, y4, mean, rstd, ymean, C,
-                     HW / 4, cs, vpt, eps, act);
+      IA_ACT_SWITCH(act, return ia_launch(ia_fwd_kernel<false, ACT_>, ud_cdiv(planes, IA_WARPS / G), 1, stream, x4, gamma,
+                                          beta, y4, mean, rstd, ymean, planes, C, HW / 4, G, cs, vpt, eps));
+    IA_ACT_SWITCH(act, return ia_launch(ia_fwd_kernel<true, ACT_>, planes * cs, cs, stream, x4, gamma, beta, y4, mean,
+                                        rstd, ymean, planes, C, HW / 4, G, cs, vpt, eps));
   }
   ia_fwd_generic_kernel<<<planes, IA_THREADS, 0, stream>>>(x, gamma, beta, y, mean, rstd, ymean, C, HW, eps, act);
   return ud_check_launch("ia_fwd_generic");
@@ -343,16 +473,18 @@ extern "C" int ud_in_act_bwd(const float* x, const float* gy, const float* gamma
   int cs = 1, vpt = 1, rc;
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) |
                          reinterpret_cast<uintptr_t>(gx)) & 15) == 0;
-  if (aligned && ia_pick(HW, IA_VMAX_BWD, &cs, &vpt)) {
+  int G = 1;
+  if (aligned && ia_pick(HW, IA_VMAX_BWD, &G, &cs, &vpt)) {
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const float4* g4 = reinterpret_cast<const float4*>(gy);
     float4* o4 = reinterpret_cast<float4*>(gx);
+    rc = UD_OK;
     if (cs == 1)
-      rc = ia_launch(ia_bwd_kernel<false>, planes, 1, stream, x4, g4, gamma, beta, mean, rstd, g_ymean, o4, s1, s2,
-                     C, HW / 4, cs, vpt, act);
+      IA_ACT_SWITCH(act, rc = ia_launch(ia_bwd_kernel<false, ACT_>, ud_cdiv(planes, IA_WARPS / G), 1, stream, x4, g4, gamma,
+                                        beta, mean, rstd, g_ymean, o4, s1, s2, planes, C, HW / 4, G, cs, vpt));
     else
-      rc = ia_launch(ia_bwd_kernel<true>, planes * cs, cs, stream, x4, g4, gamma, beta, mean, rstd, g_ymean, o4, s1,
-                     s2, C, HW / 4, cs, vpt, act);
+      IA_ACT_SWITCH(act, rc = ia_launch(ia_bwd_kernel<true, ACT_>, planes * cs, cs, stream, x4, g4, gamma, beta, mean,
+                                        rstd, g_ymean, o4, s1, s2, planes, C, HW / 4, G, cs, vpt));
     if (rc != UD_OK) return rc;
   } else {
     ia_bwd_generic_kernel<<<planes, IA_THREADS, 0, stream>>>(x, gy, gamma, beta, mean, rstd, g_ymean, gx, s1, s2, C,
