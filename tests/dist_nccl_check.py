@@ -1,0 +1,104 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity of the hot path under the engines' wrapping (SyncBatchNorm + DDP), real kernels, NCCL.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/dist_nccl_check.py
+
+Each rank runs the SyncBN-converted dynamic filters + DDP'd UDR18 hot path on its shard; rank 0 also runs the
+same model single-process on the concatenated batch (plain BatchNorm) and compares masks, outputs and the
+rank-summed parameter gradients (SURVEY.md §4 'distributed' row)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import procedural as P  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from unidefense_b200.model.modules import FrequencyDynamicFilter, SpatialDynamicFilter, MemoryEfficientSwish
+
+    C, h, w, n_per = 24, 6, 6, 3
+    ok = True
+    for kind, cls, cin, D in (("freq", FrequencyDynamicFilter, 2 * C, 6), ("spat", SpatialDynamicFilter, C, 3)):
+        torch.manual_seed(0)
+        ref = cls(C, MemoryEfficientSwish, nn.BatchNorm2d, True, False)
+        P.fill_state_dict_(ref, salt=9)
+        ref = ref.to(dev).train()
+        import copy
+        par = nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(ref)).to(dev).train()
+        g = torch.Generator().manual_seed(5)
+        X = torch.randn(world * n_per, cin, h, w, generator=g).to(dev)
+        Dm = torch.rand(world * n_per, D, h, w, generator=g).to(dev)
+        Gm = torch.randn(world * n_per, 1, h, w, generator=g).to(dev)
+        Go = torch.randn(world * n_per, cin, h, w, generator=g).to(dev)
+        sl = slice(rank * n_per, (rank + 1) * n_per)
+        x = X[sl].clone().requires_grad_()
+        o = par(x, Dm[sl])
+        ((o["mask"] * Gm[sl]).sum() + (o["out"] * Go[sl]).sum()).backward()
+        grads = torch.cat([p.grad.flatten() for p in par.parameters()])
+        dist.all_reduce(grads)                               # sum over ranks == full-batch gradient
+        masks = [torch.empty_like(o["mask"]) for _ in range(world)]
+        dist.all_gather(masks, o["mask"].detach().contiguous())
+        gxs = [torch.empty_like(x.grad) for _ in range(world)]
+        dist.all_gather(gxs, x.grad.contiguous())
+        if rank == 0:
+            xf = X.clone().requires_grad_()
+            of = ref(xf, Dm)
+            ((of["mask"] * Gm).sum() + (of["out"] * Go).sum()).backward()
+            gref = torch.cat([p.grad.flatten() for p in ref.parameters()])
+            try:
+                torch.testing.assert_close(torch.cat(masks), of["mask"].detach(), rtol=1e-4, atol=1e-5)
+                torch.testing.assert_close(torch.cat(gxs), xf.grad, rtol=2e-4, atol=2e-5 * float(xf.grad.abs().max()))
+                torch.testing.assert_close(grads, gref, rtol=2e-4, atol=2e-5 * float(gref.abs().max()))
+                torch.testing.assert_close(par.layer1[1].running_var, ref.layer1[1].running_var, rtol=1e-4, atol=1e-6)
+                print(f"[dist_nccl_check] {kind} filter: SyncBN x{world} == single-process full batch: OK", flush=True)
+            except AssertionError as e:
+                ok = False
+                print(f"[dist_nccl_check] {kind} filter FAILED: {e}", flush=True)
+
+    # whole model under DDP: one step runs, every parameter gets a gradient, ranks agree after the all-reduce
+    from unidefense_b200.model import load_model
+    torch.manual_seed(0)
+    model = load_model("UDR18")(num_classes=2, drop_rate=0.0)
+    P.fill_state_dict_(model, salt=5)
+    model = nn.SyncBatchNorm.convert_sync_batchnorm(model).to(dev).train()
+    ddp = nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
+    g = torch.Generator().manual_seed(100 + rank)
+    x = (torch.rand(4, 3, 96, 96, generator=g) * 2 - 1).to(dev)
+    labels = torch.tensor([0, 0, 1, 1], device=dev)
+    out = ddp(x)
+    from unidefense_b200 import ops
+    ld = out["loss_dict"]
+    loss = (torch.nn.functional.cross_entropy(out["cls_out"], labels) + 0.1 * ld["freq_mask"].mean()
+            + 0.1 * ld["spat_mask"].mean() + 0.1 * sum(ops.triplet_loss(f, labels) for f in ld["triplet"])
+            + 0.1 * ld["spatial"][:2].mean() + ld["freq"][:2].mean())
+    loss.backward()
+    missing = [n for n, p in model.named_parameters() if p.requires_grad and p.grad is None]
+    gsum = torch.stack([p.grad.double().abs().sum() for p in model.parameters() if p.grad is not None]).sum()
+    both = [torch.zeros_like(gsum) for _ in range(world)]
+    dist.all_gather(both, gsum)
+    if rank == 0:
+        same = all(bool(torch.equal(both[0], b)) for b in both)
+        print(f"[dist_nccl_check] DDP UDR18 step: loss {float(loss):.4f}, params without grad: {len(missing)}, "
+              f"ranks hold identical reduced grads: {same}", flush=True)
+        ok = ok and not missing and same and bool(torch.isfinite(loss))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) else 1)
+
+
+if __name__ == "__main__":
+    main()

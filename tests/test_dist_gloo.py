@@ -1,0 +1,101 @@
+"""N>1 host logic on CPU with world_size-2 gloo groups: the SyncBatchNorm statistics exchange
+of the dynamic filters (all-gather of [mean, M2, count] + Chan merge forward, all-reduce of [sum dz, sum dz*xh]
+backward) and bench.py's rank plumbing.  The CUDA statistics kernel is replaced by a torch stand-in here
+(a test double, the product path has no CPU fallback); `tests/dist_nccl_check.py` runs the real kernels on 2 GPUs."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _cpu_local_stats(proj):
+    mean = proj.mean(dim=(0, 2, 3))
+    m2 = ((proj - mean.view(1, -1, 1, 1)) ** 2).sum(dim=(0, 2, 3))
+    return mean, m2
+
+
+def _worker(rank, world, port, shards, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from unidefense_b200 import ops
+        from unidefense_b200.model import modules as M
+        ops.bn_local_stats = _cpu_local_stats           # test double for the CUDA kernel
+        bn = nn.SyncBatchNorm(shards[0].shape[1])
+        bn.train()
+        proj = shards[rank]
+        mean, rstd, count, reduce_fn = M.bn_forward_stats(bn, proj)
+        sums = torch.stack([proj.sum(dim=(0, 2, 3)), (proj ** 2).sum(dim=(0, 2, 3))])
+        red = reduce_fn(sums.clone())
+        # uneven shards: rank 1 owns more samples than rank 0
+        out[rank] = dict(mean=mean.clone(), rstd=rstd.clone(), count=count, red=red.clone(),
+                         running_mean=bn.running_mean.clone(), running_var=bn.running_var.clone(),
+                         tracked=int(bn.num_batches_tracked))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_syncbn_statistics_exchange_two_ranks():
+    g = torch.Generator().manual_seed(0)
+    full = torch.randn(5, 6, 4, 3, generator=g) * 2.0 + 0.5
+    shards = [full[:2].contiguous(), full[2:].contiguous()]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), shards, out), nprocs=2, join=True)
+    ref_bn = nn.BatchNorm2d(6)
+    ref_bn.train()
+    ref_bn(full)
+    gmean = full.mean(dim=(0, 2, 3))
+    gvar = full.var(dim=(0, 2, 3), unbiased=False)
+    for r in (0, 1):
+        o = out[r]
+        torch.testing.assert_close(o["mean"], gmean, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(o["rstd"], torch.rsqrt(gvar + 1e-5), rtol=1e-5, atol=1e-6)
+        assert o["count"] == 5 * 4 * 3
+        torch.testing.assert_close(o["running_mean"], ref_bn.running_mean, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(o["running_var"], ref_bn.running_var, rtol=1e-5, atol=1e-6)
+        assert o["tracked"] == 1
+        want = torch.stack([full.sum(dim=(0, 2, 3)), (full ** 2).sum(dim=(0, 2, 3))])
+        torch.testing.assert_close(o["red"], want, rtol=1e-5, atol=1e-5)
+
+
+def test_local_bn_needs_no_group():
+    from unidefense_b200.model import modules as M
+    from unidefense_b200 import ops
+    old = ops.bn_local_stats
+    ops.bn_local_stats = _cpu_local_stats
+    try:
+        bn = nn.BatchNorm2d(3)
+        x = torch.randn(4, 3, 2, 2)
+        mean, rstd, count, reduce_fn = M.bn_forward_stats(bn, x)
+        assert reduce_fn is None and count == 16
+        torch.testing.assert_close(mean, x.mean(dim=(0, 2, 3)))
+        bn.eval()
+        mean2, rstd2, count2, _ = M.bn_forward_stats(bn, x)
+        assert count2 == 0 and mean2 is bn.running_mean
+    finally:
+        ops.bn_local_stats = old
+
+
+def test_bench_reference_arm_only_rank0_prints():
+    """Under torchrun the reference arm runs on rank 0 alone; the other ranks exit 0 without work."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""

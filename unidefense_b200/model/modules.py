@@ -138,8 +138,9 @@ def bn_forward_stats(bn, proj):
     if group is not None:
         world = dist.get_world_size(group)
         packed = torch.cat([mean, m2, mean.new_tensor([count])])
-        gathered = torch.empty(world, packed.numel(), device=packed.device, dtype=packed.dtype)
-        dist.all_gather_into_tensor(gathered, packed, group=group)
+        parts = [torch.empty_like(packed) for _ in range(world)]
+        dist.all_gather(parts, packed, group=group)          # 2C+1 floats per rank (<= 33 KB): latency-bound
+        gathered = torch.stack(parts)
         mean, m2, tot = merge_bn_stats(gathered[:, :C], gathered[:, C:2 * C], gathered[:, 2 * C])
         count = float(tot)
 
