@@ -165,6 +165,13 @@ UD_API int ud_mask_kl_fwd(const float* pred, const float* gt, float* loss, float
 UD_API int ud_kl_div_log_target_fwd(const float* log_pred, const float* log_target, float* loss, float* g_pred,
                                     void* ws, size_t ws_bytes, int N, int M, cudaStream_t stream);
 
+/* ---- a13: FrequencyStyleTransfer (model/modules.py:35-55; no grad) --------------------------------------
+ * out = irfft2((lmda*|Fa| + (1-lmda)*|Fb|) * exp(1j*angle(Fa))), Fa/Fb = rfft2 of content/style, ortho;
+ * content, style, out [N,C,H,W]; lmda [N] (the reference draws it on the CPU in [0.5, 1)).              */
+UD_API size_t ud_freq_style_workspace_bytes(int N, int C, int H, int W);
+UD_API int ud_freq_style_transfer(const float* content, const float* style, const float* lmda, float* out, void* ws,
+                                  size_t ws_bytes, int N, int C, int H, int W, cudaStream_t stream);
+
 /* ---- a16: stencil / resampling perturbations (no grad) ---------------------------------------------
  * random_blur (model/modules.py:15-16): torchvision gaussian_blur 5x5, sigma 1.1, reflect padding.   */
 UD_API int ud_gaussian_blur5(const float* x, float* y, int planes, int H, int W, cudaStream_t stream);

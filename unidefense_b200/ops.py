@@ -481,15 +481,20 @@ def downscale_nearest(x, bottleneck_scale=0.75):
 
 
 def freq_style_transfer(content, style, lmda):
-    """FrequencyStyleTransfer (model/modules.py:43-54); lmda [B] in [0.5, 1).
-    Library composition (cuFFT + ATen) for now; the fused sm_100a kernel is the next a13 step."""
-    L.require_cuda_f32(content, style)
-    H, W = content.shape[-2:]
-    lm = lmda.reshape(-1, 1, 1, 1).to(content)
-    fa = torch.fft.rfft2(content, norm="ortho")
-    fb = torch.fft.rfft2(style, norm="ortho")
-    mix = (lm * torch.abs(fa) + (1.0 - lm) * torch.abs(fb)) * torch.exp(1j * torch.angle(fa))
-    return torch.fft.irfft2(mix, s=(H, W), norm="ortho")
+    """FrequencyStyleTransfer (model/modules.py:43-54); lmda [B] in [0.5, 1).  Fused rows / cols+mix / rows^-1
+    kernels, spectra stay in an L2-resident workspace."""
+    content, style = content.detach().contiguous(), style.detach().contiguous()
+    lm = lmda.detach().reshape(-1).to(device=content.device, dtype=torch.float32).contiguous()
+    L.require_cuda_f32(content, style, lm)
+    if content.shape != style.shape or lm.numel() != content.shape[0]:
+        raise ValueError("freq_style_transfer: content/style/lmda shapes disagree")
+    N, C, H, W = content.shape
+    lib = L.lib()
+    out = torch.empty_like(content)
+    ws = L.workspace(lib.ud_freq_style_workspace_bytes(N, C, H, W), content.device)
+    L.check(lib.ud_freq_style_transfer(L.ptr(content), L.ptr(style), L.ptr(lm), L.ptr(out), L.ptr(ws), ws.numel(), N, C,
+                                       H, W, L.stream()), "freq_style_transfer")
+    return out
 
 
 def spatial_style_transfer(content, style, lmda):
@@ -505,27 +510,34 @@ def spatial_style_transfer(content, style, lmda):
     return (cf + (1 - lm) * matched - (1 - lm) * cf).view(B, C, H, W)
 
 
-def coral_batch(source, target):
-    """coral (utils/operation.py:20-45) for every (source[n], target[n]) pair at once, without the
-    reference's per-sample python loop (model/unidefense.py:189-191).  Keeps the reference's
-    U*sqrt(D)*Vh^T 'square root' (Appendix D); the 3x3 SVDs go through the same torch.linalg.svd."""
-    L.require_cuda_f32(source, target)
-    N, C = source.shape[:2]
-    shape = source.shape
+def _coral_stats(img):
+    """utils/operation.py:6-12,:24-27 batched: normalised pixels [N,C,HW], mean, unbiased std, f f^T + I."""
+    N, C = img.shape[:2]
+    f = img.reshape(N, C, -1)
+    mean = f.mean(dim=-1, keepdim=True)
+    std = f.std(dim=-1, keepdim=True)
+    fn = (f - mean) / std
+    cov = fn @ fn.transpose(1, 2) + torch.eye(C, device=img.device, dtype=img.dtype)
+    return fn, mean, std, cov
 
-    def stats(img):
-        f = img.reshape(N, C, -1)
-        mean = f.mean(dim=-1, keepdim=True)
-        std = f.std(dim=-1, keepdim=True)
-        fn = (f - mean) / std
-        cov = fn @ fn.transpose(1, 2) + torch.eye(C, device=img.device, dtype=img.dtype)
-        return fn, mean, std, cov
 
-    def quirk_sqrt(m):
+def _coral_quirk_sqrt(covs):
+    """_mat_sqrt (operation.py:15-17) per matrix: U diag(sqrt(D)) Vh^T with torch's UNBATCHED svd."""
+    outs = []
+    for m in covs:
         U, D, Vh = torch.linalg.svd(m)
-        return U @ torch.diag_embed(D.sqrt()) @ Vh.transpose(1, 2)
+        outs.append(U @ torch.diag(D.sqrt()) @ Vh.t())
+    return torch.stack(outs)
 
-    s_n, _, _, s_cov = stats(source)
-    _, t_mean, t_std, t_cov = stats(target)
-    m = quirk_sqrt(t_cov) @ torch.linalg.inv(quirk_sqrt(s_cov))
-    return ((m @ s_n) * t_std + t_mean).view(shape)
+
+def coral_batch(source, target):
+    """coral (utils/operation.py:20-45) for every (source[n], target[n]) pair: statistics, 3x3 algebra and the
+    colour transform are batched (no per-sample python loop over images as in model/unidefense.py:189-191).
+    The reference's 'square root' U*sqrt(D)*Vh^T (Appendix D) is NOT invariant to the sign convention of the
+    SVD (fp32 vs fp64 LAPACK already disagree by O(1)), so the 2N tiny factorisations go through the same
+    unbatched torch.linalg.svd call the reference makes on this device."""
+    L.require_cuda_f32(source, target)
+    s_n, _, _, s_cov = _coral_stats(source)
+    _, t_mean, t_std, t_cov = _coral_stats(target)
+    m = _coral_quirk_sqrt(t_cov) @ torch.linalg.inv(_coral_quirk_sqrt(s_cov))
+    return ((m @ s_n) * t_std + t_mean).view(source.shape)
