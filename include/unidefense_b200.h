@@ -179,6 +179,21 @@ UD_API int ud_gaussian_blur5(const float* x, float* y, int planes, int H, int W,
 UD_API int ud_downscale_nearest(const float* x, float* y, int planes, int H, int W, float bottleneck_scale,
                                 cudaStream_t stream);
 
+/* ---- a17 (next row, first step): glue of the SFConv frequency branch ----------------------------------
+ * (model/efficientnet/exp.py:55-65, model/resnet/exp.py:44-54).  spec: interleaved complex64 [N,C,P]
+ * (P = h*(w/2+1), torch.fft.rfft2's output); planar: cat([re, im], 1) as [N,2C,P], fp32 or bf16 (bf16=1),
+ * NCHW or channels-last [N,P,2C] (nhwc=1, C even).  pack and unpack are each other's autograd adjoint.      */
+UD_API int ud_sf_pack(const void* spec, void* planar, int N, int C, int P, int nhwc, int bf16, cudaStream_t stream);
+UD_API int ud_sf_unpack(const void* planar, void* spec, int N, int C, int P, int nhwc, int bf16, cudaStream_t stream);
+/* out = (1-s)*spat + s*freq, s = sigmoid(*coef) (exp.py:64-65 / :53-54).  spat, out (and their gradients):
+ * dtype/layout per (bf16, nhwc); freq, g_freq: fp32 NCHW [N,C,P].                                           */
+UD_API int ud_sf_mix_fwd(const void* spat, const float* freq, const float* coef, void* out, int N, int C, int P,
+                         int nhwc, int bf16, cudaStream_t stream);
+UD_API size_t ud_sf_mix_bwd_workspace_bytes(int N, int C, int P);
+UD_API int ud_sf_mix_bwd(const void* g_out, const void* spat, const float* freq, const float* coef, void* g_spat,
+                         float* g_freq, float* g_coef, void* ws, size_t ws_bytes, int N, int C, int P, int nhwc,
+                         int bf16, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

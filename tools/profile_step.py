@@ -29,6 +29,9 @@ def main():
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
     model = bench.init_live(load_model(name)(**kw)).to(dev).train()
+    for part in ("backbone", "extractor", "emb_block1", "emb_block2"):
+        if hasattr(model, part):
+            getattr(model, part).to(memory_format=torch.channels_last)
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=5e-6, amsgrad=True,
                             fused=True)
     x, labels = bench.synth(nb, res, 0, dev)

@@ -58,6 +58,11 @@ SIGNATURES = {
     "ud_freq_style_transfer": (c_i, [c_p] * 5 + [c_sz] + [c_i] * 4 + [c_p]),
     "ud_gaussian_blur5": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "ud_downscale_nearest": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_p]),
+    "ud_sf_pack": (c_i, [c_p, c_p] + [c_i] * 5 + [c_p]),
+    "ud_sf_unpack": (c_i, [c_p, c_p] + [c_i] * 5 + [c_p]),
+    "ud_sf_mix_fwd": (c_i, [c_p] * 4 + [c_i] * 5 + [c_p]),
+    "ud_sf_mix_bwd_workspace_bytes": (c_sz, [c_i] * 3),
+    "ud_sf_mix_bwd": (c_i, [c_p] * 8 + [c_sz] + [c_i] * 5 + [c_p]),
     "ud_kl_div_log_target_fwd": (c_i, [c_p] * 5 + [c_sz, c_i, c_i, c_p]),
 }
 

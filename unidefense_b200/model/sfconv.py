@@ -18,24 +18,36 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-# on CUDA, feature maps up to 64x64 (every SFConv layer of the three models except the single
-# 95x95 one of EfficientNet-B4 @380) take the fused shared-memory rFFT2 / irFFT2 kernels of the hot path
-# (ops.rfft2_cat / ops.irfft2_cat write the cat([re, im]) layout the 1x1 conv consumes directly, with the exact
-# fft_r2c / fft_c2r autograd adjoints) instead of cuFFT + real/imag/cat/complex/tensor_split passes.
-USE_FFT_KERNELS = os.environ.get("UD_SFCONV_KERNELS", "0") == "1"   # opt-in: the direct-DFT kernels lose to cuFFT at 24x24+ (profiles/)
-_KERNEL_MAX = 64
+# SURVEY.md §8(f) #1, first step: on CUDA the ~10 elementwise / layout / dtype passes torch makes around the two
+# FFTs and the 1x1 convolution (x.float, real, imag, cat, cast, tensor_split, complex, two muls, add and their
+# backward twins) are replaced by three single-pass kernels (ops.sf_pack / sf_unpack / sf_mix); cuFFT and the
+# convolution stay library calls.  UD_SFCONV_GLUE=0 restores the plain composition (used by the CPU oracle arm).
+USE_GLUE_KERNELS = os.environ.get("UD_SFCONV_GLUE", "1") != "0"
+
+
+def _sf_forward(x, spat, freq_conv, sf_coef, norm):
+    """(1 - sigmoid(sf_coef)) * spat + sigmoid(sf_coef) * pool(irfft2(freq_conv(cat rfft2(x))))."""
+    size = x.shape[-2:]
+    if USE_GLUE_KERNELS and x.is_cuda:
+        from .. import ops
+        xf = x.to(dtype=torch.float32, memory_format=torch.contiguous_format)
+        with torch.autocast(device_type="cuda", enabled=False):
+            spec = torch.fft.rfft2(xf, norm=norm)
+        cl = spat.dim() == 4 and spat.is_contiguous(memory_format=torch.channels_last) and not spat.is_contiguous()
+        planar = ops.sf_pack(spec, spat.dtype if spat.dtype in (torch.float32, torch.bfloat16) else torch.float32, cl)
+        planar = freq_conv(planar)
+        with torch.autocast(device_type="cuda", enabled=False):
+            y = torch.fft.irfft2(ops.sf_unpack(planar), s=size, norm=norm)
+        if tuple(y.shape[-2:]) != tuple(spat.shape[-2:]):
+            y = F.adaptive_avg_pool2d(y, spat.shape[-2:])
+        return ops.sf_mix(spat, y, sf_coef)
+    freq = _freq_branch(x, freq_conv, spat.shape[-2:], norm)
+    gate = torch.sigmoid(sf_coef)
+    return (1.0 - gate) * spat + gate * freq
 
 
 def _freq_branch(x, freq_conv, out_hw, norm):
     size = x.shape[-2:]
-    if USE_FFT_KERNELS and x.is_cuda and size[0] <= _KERNEL_MAX and size[1] <= _KERNEL_MAX and norm in ("ortho", None):
-        from .. import ops
-        planar = ops.rfft2_cat(x.float(), norm)
-        planar = freq_conv(planar)
-        y = ops.irfft2_cat(planar.float(), size, norm)
-        if tuple(y.shape[-2:]) != tuple(out_hw):
-            y = F.adaptive_avg_pool2d(y, out_hw)
-        return y
     with torch.autocast(device_type=x.device.type, enabled=False):
         spec = torch.fft.rfft2(x.float(), norm=norm)
         planar = torch.cat([spec.real, spec.imag], dim=1)
@@ -59,9 +71,7 @@ class SFConv2d(nn.Conv2d):
 
     def forward(self, x):
         spat = self._conv_forward(x, self.weight, self.bias)
-        freq = _freq_branch(x, self.freq_conv, spat.shape[-2:], self.freq_norm)
-        gate = torch.sigmoid(self.sf_coef)
-        return (1.0 - gate) * spat + gate * freq
+        return _sf_forward(x, spat, self.freq_conv, self.sf_coef, self.freq_norm)
 
 
 def same_pad_amounts(size, kernel, stride, dilation=1):
@@ -98,6 +108,4 @@ class SFSamePadConv2d(SamePadConv2d):
 
     def forward(self, x):
         spat = self._conv_forward(self.static_padding(x), self.weight, self.bias)
-        freq = _freq_branch(x, self.freq_conv, spat.shape[-2:], self.freq_norm)
-        gate = torch.sigmoid(self.sf_coef)
-        return (1.0 - gate) * spat + gate * freq
+        return _sf_forward(x, spat, self.freq_conv, self.sf_coef, self.freq_norm)

@@ -541,3 +541,121 @@ def coral_batch(source, target):
     _, t_mean, t_std, t_cov = _coral_stats(target)
     m = _coral_quirk_sqrt(t_cov) @ torch.linalg.inv(_coral_quirk_sqrt(s_cov))
     return ((m @ s_n) * t_std + t_mean).view(source.shape)
+
+
+# ------------------------------------------------------------------------------------------
+# a17 (next row, first step): glue kernels of the SFConv frequency branch
+# ------------------------------------------------------------------------------------------
+def _fmt(t):
+    """-> (nhwc, bf16) of a 4-D activation; anything else is made NCHW-contiguous fp32 by the caller."""
+    nhwc = t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+    return int(nhwc), int(t.dtype == torch.bfloat16)
+
+
+class _SfPack(torch.autograd.Function):
+    """complex64 spectrum [N,C,h,wh] -> planar cat([re, im], 1) [N,2C,h,wh] in `dtype` / `channels_last`."""
+
+    @staticmethod
+    def forward(ctx, spec, dtype, channels_last):
+        spec = spec.contiguous()
+        if not spec.is_cuda or spec.dtype != torch.complex64:
+            raise RuntimeError("sf_pack needs a CUDA complex64 spectrum (no CPU fallback)")
+        N, C, h, wh = spec.shape
+        nhwc = int(bool(channels_last) and C % 2 == 0)
+        planar = torch.empty(N, 2 * C, h, wh, device=spec.device, dtype=dtype,
+                             memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+        L.check(L.lib().ud_sf_pack(L.ptr(spec), L.ptr(planar), N, C, h * wh, nhwc, int(dtype == torch.bfloat16),
+                                   L.stream()), "sf_pack")
+        return planar
+
+    @staticmethod
+    def backward(ctx, g):
+        return _sf_unpack_raw(g), None, None
+
+
+def _sf_unpack_raw(planar):
+    N, C2, h, wh = planar.shape
+    C = C2 // 2
+    if planar.dtype not in (torch.float32, torch.bfloat16):
+        planar = planar.float()
+    nhwc, bf16 = _fmt(planar)
+    if not nhwc:
+        planar = planar.contiguous()
+    elif C % 2:
+        planar, nhwc = planar.contiguous(), 0
+    spec = torch.empty(N, C, h, wh, device=planar.device, dtype=torch.complex64)
+    L.check(L.lib().ud_sf_unpack(L.ptr(planar), L.ptr(spec), N, C, h * wh, nhwc, bf16, L.stream()), "sf_unpack")
+    return spec
+
+
+class _SfUnpack(torch.autograd.Function):
+    """planar [N,2C,h,wh] (fp32|bf16, NCHW|channels-last) -> complex64 [N,C,h,wh]."""
+
+    @staticmethod
+    def forward(ctx, planar):
+        if not planar.is_cuda:
+            raise RuntimeError("sf_unpack needs CUDA tensors (no CPU fallback)")
+        ctx.dtype = planar.dtype
+        ctx.cl = bool(_fmt(planar)[0])
+        return _sf_unpack_raw(planar)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _SfPack.apply(g, ctx.dtype, ctx.cl)
+
+
+def sf_pack(spec, dtype=torch.float32, channels_last=False):
+    return _SfPack.apply(spec, dtype, channels_last)
+
+
+def sf_unpack(planar):
+    return _SfUnpack.apply(planar)
+
+
+class _SfMix(torch.autograd.Function):
+    """(1 - sigmoid(coef)) * spat + sigmoid(coef) * freq; spat in the convolution's dtype/layout, freq fp32 NCHW."""
+
+    @staticmethod
+    def forward(ctx, spat, freq, coef):
+        if not spat.is_cuda:
+            raise RuntimeError("sf_mix needs CUDA tensors (no CPU fallback)")
+        if spat.dtype not in (torch.float32, torch.bfloat16):
+            spat = spat.float()
+        nhwc, bf16 = _fmt(spat)
+        N, C = spat.shape[:2]
+        if nhwc and C % 2:
+            nhwc = 0
+        if not nhwc:
+            spat = spat.contiguous()
+        freq = freq.contiguous()
+        c = coef.reshape(1).contiguous()
+        L.require_cuda_f32(freq, c)
+        P = spat.shape[2] * spat.shape[3]
+        out = torch.empty_like(spat)
+        L.check(L.lib().ud_sf_mix_fwd(L.ptr(spat), L.ptr(freq), L.ptr(c), L.ptr(out), N, C, P, nhwc, bf16, L.stream()),
+                "sf_mix_fwd")
+        ctx.save_for_backward(spat, freq, c)
+        ctx.fmt = (nhwc, bf16)
+        ctx.coef_shape = coef.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        spat, freq, c = ctx.saved_tensors
+        nhwc, bf16 = ctx.fmt
+        N, C = spat.shape[:2]
+        P = spat.shape[2] * spat.shape[3]
+        g = g.to(spat.dtype)
+        g = g.contiguous(memory_format=torch.channels_last) if nhwc else g.contiguous()
+        lib = L.lib()
+        g_spat = torch.empty_like(spat)
+        g_freq = torch.empty_like(freq)
+        g_coef = torch.empty(1, device=spat.device, dtype=torch.float32)
+        ws = L.workspace(lib.ud_sf_mix_bwd_workspace_bytes(N, C, P), spat.device)
+        L.check(lib.ud_sf_mix_bwd(L.ptr(g), L.ptr(spat), L.ptr(freq), L.ptr(c), L.ptr(g_spat), L.ptr(g_freq), L.ptr(g_coef),
+                                  L.ptr(ws), ws.numel(), N, C, P, nhwc, bf16, L.stream()), "sf_mix_bwd")
+        return g_spat, g_freq, g_coef.reshape(ctx.coef_shape)
+
+
+def sf_mix(spat, freq, coef):
+    return _SfMix.apply(spat, freq, coef)
