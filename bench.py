@@ -274,15 +274,16 @@ def run_ours(args):
     else:
         ddp = model
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.999), weight_decay=5e-6, amsgrad=True, fused=True)
+    use_graph = args.graph != "off"
+    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.999), weight_decay=5e-6, amsgrad=True, fused=True,
+                            capturable=use_graph)
     x_host, l_host = synth(nb, res, rank, pin=True)
     x_dev, l_dev = x_host.to(dev), l_host.to(dev)
     nr = nb // 2
     amp = args.dtype == "bf16"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def step(x, labels):
-        opt.zero_grad(set_to_none=True)
+    def body(x, labels):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
             out = ddp(x)
         ld = out["loss_dict"]
@@ -293,6 +294,49 @@ def run_ours(args):
         loss.backward()
         opt.step()
         return loss
+
+    def eager_step(x, labels):
+        opt.zero_grad(set_to_none=True)
+        return body(x, labels)
+
+    step = eager_step
+    graph_note = "off"
+    if use_graph:
+        # Whole-step CUDA graph (forward, loss, backward incl. DDP/SyncBN NCCL collectives, fused AdamW): the step
+        # issues ~3000 small kernels and is host-launch-bound, worst with 8 ranks sharing the box's cores.
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(11 if world > 1 else 3):      # DDP needs 11 side-stream iterations before capture
+                    eager_step(x_dev, l_dev)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            l0 = L.lib().ud_launch_count()
+            with torch.cuda.graph(graph):
+                static_loss = body(x_dev, l_dev)
+            graph_launches = L.lib().ud_launch_count() - l0
+            graph.replay()
+            torch.cuda.synchronize()
+            if not bool(torch.isfinite(static_loss)):
+                raise RuntimeError("non-finite loss after graph replay")
+
+            def step(x, labels):
+                if x is not x_dev:
+                    x_dev.copy_(x, non_blocking=True)
+                    l_dev.copy_(labels, non_blocking=True)
+                graph.replay()
+                return static_loss
+            graph_note = "whole step captured"
+        except Exception as e:                       # fall back to eager launches, say so in the JSON line
+            if args.graph == "on":
+                raise
+            graph_note = f"capture failed, eager ({type(e).__name__}: {str(e)[:120]})"
+            torch.cuda.synchronize()
+            step = eager_step
+            use_graph = False
 
     def barrier():
         if world > 1:
@@ -308,7 +352,8 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    L.PROFILE = {}
+    graphed = graph_note == "whole step captured"
+    L.PROFILE = None if graphed else {}
     launches0 = L.lib().ud_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -317,18 +362,29 @@ def run_ours(args):
         step(x_dev, l_dev)
     e1.record()
     barrier()
-    launches = L.lib().ud_launch_count() - launches0
-    prof = L.profile_summary()
-    L.PROFILE = None
+    launches = graph_launches * args.steps if graphed else L.lib().ud_launch_count() - launches0
     ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.summary()
+    if graphed:
+        # events cannot be recorded inside a replayed graph: the per-op device times behind `roofline` come from
+        # the same step issued eagerly right after the timed region (same inputs, same kernels, L2 flushed)
+        L.PROFILE = {}
+        for _ in range(args.steps):
+            flush.zero_()
+            eager_step(x_dev, l_dev)
+        torch.cuda.synchronize()
+    prof = L.profile_summary()
+    L.PROFILE = None
 
     # end to end through the public API with HOST buffers: pinned H2D of the batch + D2H of the loss every step
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()
-        loss = step(x_host.to(dev, non_blocking=True), l_host.to(dev, non_blocking=True))
+        if graphed:
+            loss = step(x_host, l_host)                      # H2D straight into the graph's static input buffers
+        else:
+            loss = step(x_host.to(dev, non_blocking=True), l_host.to(dev, non_blocking=True))
         loss_host = loss.item()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -357,7 +413,8 @@ def run_ours(args):
                     "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4), "traffic": TRAFFIC.get(dom),
                     "alg_bytes_per_launch": ab[dom] // max(prof[dom][0] // args.steps, 1),
                     "ms_per_step_in_kernel": round(ops_ms[dom], 4)}
-        hot_ms = sum(ops_ms.values())
+        sf_ms = sum(v for k, v in ops_ms.items() if k.startswith("sf_"))     # SFConv glue (backbone, §8f) -- not recon path
+        hot_ms = sum(ops_ms.values()) - sf_ms
         mbs = RECON_MB_PER_SAMPLE.get((arch, res))
         line = {"metric": METRIC, "value": round(nb * world / (ms * 1e-3), 2), "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
@@ -367,6 +424,7 @@ def run_ours(args):
                            "hot_path_dtype": "f32", "backbone": f"stock torch, {args.dtype} autocast"
                                        + (f", channels_last ({args.channels_last})" if args.channels_last != "none" else ""),
                            "parallelism": f"dp{world}" + (" (DDP + SyncBatchNorm, NCCL)" if world > 1 else ""),
+                           "cuda_graph": graph_note,
                            "l2": "256 MB buffer written between timed iterations; per-step activations >> 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": round(nb * world / (e2e_ms * 1e-3), 2), "unit": "samples/s",
@@ -375,6 +433,7 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "roofline": roof,
                 "hot_path": {"kernel_ms_per_step": round(hot_ms, 3), "share_of_step": round(hot_ms / ms, 4),
+                             "sfconv_glue_kernel_ms_per_step": round(sf_ms, 3),
                              "alg_mb_per_sample": mbs,
                              "hbm_frac_of_recon_path_kernels": (round(mbs * 1e6 * nb / (hot_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4)
                                                                 if mbs else None),
@@ -417,6 +476,8 @@ def main():
     ap.add_argument("--channels-last", default="backbone", choices=["none", "all", "backbone"],
                     help="memory format of the stock-torch convolutions (the hot-path kernels are NCHW)")
     ap.add_argument("--cpu-sample", type=int, default=4, help="faces per CPU step of the reference / cpu_baseline leg")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="capture the whole training step in a CUDA graph (auto: fall back to eager if capture fails)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recon-probe", action="store_true")
     ap.add_argument("--recon-only", action="store_true", help="run only the isolated recon-path probe (profiling aid)")

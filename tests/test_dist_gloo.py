@@ -44,7 +44,7 @@ def _worker(rank, world, port, shards, out):
         sums = torch.stack([proj.sum(dim=(0, 2, 3)), (proj ** 2).sum(dim=(0, 2, 3))])
         red = reduce_fn(sums.clone())
         # uneven shards: rank 1 owns more samples than rank 0
-        out[rank] = dict(mean=mean.clone(), rstd=rstd.clone(), count=count, red=red.clone(),
+        out[rank] = dict(mean=mean.clone(), rstd=rstd.clone(), count=float(count), red=red.clone(),
                          running_mean=bn.running_mean.clone(), running_var=bn.running_var.clone(),
                          tracked=int(bn.num_batches_tracked))
     finally:

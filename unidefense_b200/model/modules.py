@@ -124,7 +124,8 @@ def merge_bn_stats(means, m2s, counts):
 
 
 def bn_forward_stats(bn, proj):
-    """-> (mean [C], rstd [C], count, stat_reduce).  Training: batch statistics (merged over ranks
+    """-> (mean [C], rstd [C], count, stat_reduce); `count` is a python float locally and a 0-dim DEVICE tensor
+    under SyncBatchNorm (no host sync, CUDA-graph capturable).  Training: batch statistics (merged over ranks
     when `bn` is a SyncBatchNorm inside an initialised process group, engine/forgery_engine.py:142)
     and the running-stat update of nn.BatchNorm2d (momentum, unbiased variance).  Eval: running stats."""
     use_batch = bn.training or bn.running_mean is None
@@ -141,8 +142,7 @@ def bn_forward_stats(bn, proj):
         parts = [torch.empty_like(packed) for _ in range(world)]
         dist.all_gather(parts, packed, group=group)          # 2C+1 floats per rank (<= 33 KB): latency-bound
         gathered = torch.stack(parts)
-        mean, m2, tot = merge_bn_stats(gathered[:, :C], gathered[:, C:2 * C], gathered[:, 2 * C])
-        count = float(tot)
+        mean, m2, count = merge_bn_stats(gathered[:, :C], gathered[:, C:2 * C], gathered[:, 2 * C])
 
         def reduce_fn(t):
             t = t.contiguous()
@@ -154,8 +154,9 @@ def bn_forward_stats(bn, proj):
             bn.num_batches_tracked += 1
             mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
             bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
-            bn.running_var.mul_(1 - mom).add_(m2 / max(count - 1.0, 1.0), alpha=mom)
-    return mean, torch.rsqrt(var + bn.eps), int(count), reduce_fn
+            denom = (count - 1.0).clamp(min=1.0) if torch.is_tensor(count) else max(count - 1.0, 1.0)
+            bn.running_var.mul_(1 - mom).add_(m2 / denom, alpha=mom)
+    return mean, torch.rsqrt(var + bn.eps), (count if torch.is_tensor(count) else int(count)), reduce_fn
 
 
 class _DynamicFilter(nn.Module):

@@ -342,10 +342,16 @@ class _DyfiMask(torch.autograd.Function):
         L.check(lib.ud_bn_bwd_reduce(L.ptr(dz), L.ptr(proj), L.ptr(mean), L.ptr(rstd), L.ptr(sums[0]), L.ptr(sums[1]),
                                      N, Cp, HW, L.stream()), "bn_bwd_reduce")
         g_beta, g_gamma = sums[0].clone(), sums[1].clone()      # local sums: DDP averages parameter grads
-        if ctx.stat_reduce is not None and ctx.count:
+        count = ctx.count
+        training = torch.is_tensor(count) or bool(count)
+        if ctx.stat_reduce is not None and training:
             sums = ctx.stat_reduce(sums)
         g_proj = torch.empty_like(proj)
-        inv_count = 1.0 / ctx.count if ctx.count else 0.0
+        if torch.is_tensor(count):           # cross-rank count lives on the device: fold 1/count into the sums
+            sums = sums / count
+            inv_count = 1.0
+        else:
+            inv_count = 1.0 / count if count else 0.0
         L.check(lib.ud_bn_bwd_apply(L.ptr(dz), L.ptr(proj), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(sums[0]),
                                     L.ptr(sums[1]), inv_count, L.ptr(g_proj), N, Cp, HW, L.stream()), "bn_bwd_apply")
         return (g_proj, None, None, g_gamma if gamma is not None else None, g_beta if beta is not None else None,
@@ -354,8 +360,8 @@ class _DyfiMask(torch.autograd.Function):
 
 def dyfi_mask(proj, mean, rstd, gamma, beta, diff, w2, x, act="swish", count=0, want_out=True, stat_reduce=None):
     """-> (mask [N,1,h,w], out = mask*x or None)."""
-    return _DyfiMask.apply(proj, mean, rstd, gamma, beta, diff, w2, x, ACT_CODES[act], int(count), bool(want_out),
-                           stat_reduce)
+    return _DyfiMask.apply(proj, mean, rstd, gamma, beta, diff, w2, x, ACT_CODES[act],
+                           count if torch.is_tensor(count) else int(count), bool(want_out), stat_reduce)
 
 
 # ------------------------------------------------------------------------------------------
