@@ -274,7 +274,9 @@ def run_ours(args):
     else:
         ddp = model
     params = [p for p in model.parameters() if p.requires_grad]
-    use_graph = args.graph != "off"
+    # whole-step CUDA graph: validated single-GPU; under DDP the NCCL capture dead-locked on this stack (round 1),
+    # so multi-GPU runs stay eager unless --graph on is forced
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
     opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.999), weight_decay=5e-6, amsgrad=True, fused=True,
                             capturable=use_graph)
     x_host, l_host = synth(nb, res, rank, pin=True)
@@ -300,7 +302,7 @@ def run_ours(args):
         return body(x, labels)
 
     step = eager_step
-    graph_note = "off"
+    graph_note = "off" if world == 1 or args.graph == "off" else "off (eager under DDP: NCCL capture not validated)"
     if use_graph:
         # Whole-step CUDA graph (forward, loss, backward incl. DDP/SyncBN NCCL collectives, fused AdamW): the step
         # issues ~3000 small kernels and is host-launch-bound, worst with 8 ranks sharing the box's cores.
