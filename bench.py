@@ -250,7 +250,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    ddp_graph = world > 1 and (args.graph == "on" or os.environ.get("UD_BENCH_DDP_GRAPH", "0") == "1")
     if world > 1:
+        if ddp_graph:   # whole-network capture with DDP: no NCCL watchdog event queries while a stream captures
+            os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
+            os.environ["NCCL_ASYNC_ERROR_HANDLING"] = "0"
         dist.init_process_group("nccl", device_id=dev)
     from unidefense_b200 import _lib as L
     from unidefense_b200 import ops
@@ -269,14 +273,21 @@ def run_ours(args):
             if hasattr(model, part):
                 getattr(model, part).to(memory_format=torch.channels_last)
     if world > 1:                                             # engine/forgery_engine.py:142-145
-        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
+        if args.syncbn == "torch":
+            model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+        else:       # same math and collectives, without torch's per-layer device->host sync (unidefense_b200/parallel.py)
+            from unidefense_b200.parallel import convert_sync_batchnorm
+            model = convert_sync_batchnorm(model)
+        ctor_stream = torch.cuda.Stream() if ddp_graph else torch.cuda.current_stream()
+        with torch.cuda.stream(ctor_stream):       # DDP must be built on a side stream to be capturable later
+            ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
+        torch.cuda.current_stream().wait_stream(ctor_stream)
     else:
         ddp = model
     params = [p for p in model.parameters() if p.requires_grad]
     # whole-step CUDA graph: validated single-GPU; under DDP the NCCL capture dead-locked on this stack (round 1),
     # so multi-GPU runs stay eager unless --graph on is forced
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    use_graph = (args.graph != "off" and world == 1) or ddp_graph
     opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.999), weight_decay=5e-6, amsgrad=True, fused=True,
                             capturable=use_graph)
     x_host, l_host = synth(nb, res, rank, pin=True)
@@ -317,9 +328,20 @@ def run_ours(args):
             graph = torch.cuda.CUDAGraph()
             opt.zero_grad(set_to_none=True)
             l0 = L.lib().ud_launch_count()
-            with torch.cuda.graph(graph):
-                static_loss = body(x_dev, l_dev)
+            err = None
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    static_loss = body(x_dev, l_dev)
+            except Exception as e:                   # noqa: BLE001
+                err = e
             graph_launches = L.lib().ud_launch_count() - l0
+            if world > 1:                            # every rank replays, or none does (else the collectives dead-lock)
+                flag = torch.tensor([0.0 if err is not None else 1.0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if float(flag) == 0.0 and err is None:
+                    err = RuntimeError("capture failed on another rank")
+            if err is not None:
+                raise err
             graph.replay()
             torch.cuda.synchronize()
             if not bool(torch.isfinite(static_loss)):
@@ -333,7 +355,7 @@ def run_ours(args):
                 return static_loss
             graph_note = "whole step captured"
         except Exception as e:                       # fall back to eager launches, say so in the JSON line
-            if args.graph == "on":
+            if args.graph == "on" and world == 1:
                 raise
             graph_note = f"capture failed, eager ({type(e).__name__}: {str(e)[:120]})"
             torch.cuda.synchronize()
@@ -425,7 +447,7 @@ def run_ours(args):
                                        f"{res}x{res}, per-GPU batch {nb}, random init",
                            "hot_path_dtype": "f32", "backbone": f"stock torch, {args.dtype} autocast"
                                        + (f", channels_last ({args.channels_last})" if args.channels_last != "none" else ""),
-                           "parallelism": f"dp{world}" + (" (DDP + SyncBatchNorm, NCCL)" if world > 1 else ""),
+                           "parallelism": f"dp{world}" + (f" (DDP + SyncBatchNorm[{args.syncbn}], NCCL)" if world > 1 else ""),
                            "cuda_graph": graph_note,
                            "l2": "256 MB buffer written between timed iterations; per-step activations >> 126 MB L2"},
                 "clocks": clocks,
@@ -480,6 +502,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="faces per CPU step of the reference / cpu_baseline leg")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the whole training step in a CUDA graph (auto: fall back to eager if capture fails)")
+    ap.add_argument("--syncbn", default="ours", choices=["ours", "torch"],
+                    help="multi-GPU BatchNorm conversion: torch.nn.SyncBatchNorm or the host-sync-free equivalent")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recon-probe", action="store_true")
     ap.add_argument("--recon-only", action="store_true", help="run only the isolated recon-path probe (profiling aid)")

@@ -68,12 +68,46 @@ def main():
                 ok = False
                 print(f"[dist_nccl_check] {kind} filter FAILED: {e}", flush=True)
 
+    # host-sync-free SyncBatchNorm (unidefense_b200/parallel.py) == torch.nn.SyncBatchNorm on the same shards
+    from unidefense_b200.parallel import convert_sync_batchnorm
+    for cl in (False, True):
+        torch.manual_seed(3)
+        base = nn.Sequential(nn.Conv2d(6, 16, 3, padding=1, bias=False), nn.BatchNorm2d(16), nn.ReLU(),
+                             nn.Conv2d(16, 8, 1, bias=False), nn.BatchNorm2d(8, momentum=0.01, eps=1e-3)).to(dev)
+        import copy
+        a = nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(base)).train()
+        b = convert_sync_batchnorm(copy.deepcopy(base)).train()
+        g = torch.Generator().manual_seed(40 + rank)
+        xin = torch.randn(3 + rank, 6, 9, 7, generator=g).to(dev)          # uneven per-rank batch
+        gout = torch.randn(3 + rank, 8, 9, 7, generator=g).to(dev)
+        if cl:
+            a, b = a.to(memory_format=torch.channels_last), b.to(memory_format=torch.channels_last)
+            xin = xin.contiguous(memory_format=torch.channels_last)
+        outs = []
+        for net in (a, b):
+            xi = xin.clone().requires_grad_()
+            y = net(xi)
+            (y * gout).sum().backward()
+            outs.append((y.detach(), xi.grad, [p.grad for p in net.parameters()], [bf.clone() for bf in net.buffers()]))
+        try:
+            torch.testing.assert_close(outs[1][0], outs[0][0], rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(outs[1][1], outs[0][1], rtol=1e-5, atol=1e-6)
+            for u, v in zip(outs[1][2], outs[0][2]):
+                torch.testing.assert_close(u, v, rtol=1e-5, atol=1e-6)
+            for u, v in zip(outs[1][3], outs[0][3]):
+                torch.testing.assert_close(u, v, rtol=1e-5, atol=1e-6)
+            if rank == 0:
+                print(f"[dist_nccl_check] parallel.SyncBatchNorm == torch SyncBatchNorm (channels_last={cl}): OK", flush=True)
+        except AssertionError as e:
+            ok = False
+            print(f"[dist_nccl_check] parallel.SyncBatchNorm FAILED on rank {rank} (channels_last={cl}): {e}", flush=True)
+
     # whole model under DDP: one step runs, every parameter gets a gradient, ranks agree after the all-reduce
     from unidefense_b200.model import load_model
     torch.manual_seed(0)
     model = load_model("UDR18")(num_classes=2, drop_rate=0.0)
     P.fill_state_dict_(model, salt=5)
-    model = nn.SyncBatchNorm.convert_sync_batchnorm(model).to(dev).train()
+    model = convert_sync_batchnorm(model).to(dev).train()
     ddp = nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
     g = torch.Generator().manual_seed(100 + rank)
     x = (torch.rand(4, 3, 96, 96, generator=g) * 2 - 1).to(dev)
@@ -95,7 +129,7 @@ def main():
               f"ranks hold identical reduced grads: {same}", flush=True)
         ok = ok and not missing and same and bool(torch.isfinite(loss))
     flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     sys.exit(0 if int(flag) else 1)
 

@@ -85,3 +85,28 @@ def test_merge_bn_stats_matches_global_statistics():
     torch.testing.assert_close(mean, allx.mean(0))
     torch.testing.assert_close(m2, ((allx - allx.mean(0)) ** 2).sum(0))
     assert float(n) == 22
+
+
+def test_parallel_sync_batchnorm_conversion_cpu():
+    """unidefense_b200.parallel.convert_sync_batchnorm: same tree/keys as torch's converter, BatchNorm semantics
+    when no process group is initialised (the 2-GPU equivalence with torch.nn.SyncBatchNorm is checked by
+    tests/dist_nccl_check.py)."""
+    from unidefense_b200.parallel import SyncBatchNorm, convert_sync_batchnorm
+    model = _build("r18")
+    keys = list(model.state_dict().keys())
+    n_bn = sum(isinstance(m, nn.modules.batchnorm._BatchNorm) for m in model.modules())
+    conv = convert_sync_batchnorm(model)
+    assert list(conv.state_dict().keys()) == keys
+    assert sum(isinstance(m, SyncBatchNorm) for m in conv.modules()) == n_bn
+    assert isinstance(conv.freq_filter.layer1[1], nn.SyncBatchNorm)          # what model/modules.py keys its sync on
+    assert not conv.bottleneck.bias.requires_grad                            # frozen bias survives (shared Parameter)
+    assert convert_sync_batchnorm(conv) is conv and sum(isinstance(m, SyncBatchNorm) for m in conv.modules()) == n_bn
+    bn = nn.BatchNorm2d(4, momentum=0.01, eps=1e-3)
+    sb = convert_sync_batchnorm(nn.Sequential(bn))[0]
+    ref = nn.BatchNorm2d(4, momentum=0.01, eps=1e-3)
+    ref.load_state_dict(sb.state_dict())
+    x = torch.randn(3, 4, 5, 5)
+    torch.testing.assert_close(sb(x), ref(x))
+    torch.testing.assert_close(sb.running_var, ref.running_var)
+    sb.eval(); ref.eval()
+    torch.testing.assert_close(sb(x), ref(x))
