@@ -93,24 +93,53 @@ def test_sfconv_modules_reference_fixture(golden_ops, cl):
         assert m.sf_coef.grad is not None and m.weight.grad is not None
 
 
-def test_sfconv_glue_equals_plain_composition_bf16():
-    """bf16 autocast + channels_last (the bench configuration): glue kernels vs the plain torch composition."""
+@pytest.mark.parametrize("cfg", [(48, 24, 5, 2), (32, 12, 3, 1), (16, 48, 3, 1)])
+def test_sfconv_paths_agree_bf16(cfg):
+    """bf16 autocast + channels_last (the bench configuration): DFT-by-GEMM path and glue-kernel path vs the plain
+    torch composition (bf16 tolerance: the twiddles themselves are bf16 in the GEMM path)."""
     from unidefense_b200.model import sfconv
+    C, hw, k, stride = cfg
     torch.manual_seed(0)
-    m = sfconv.SFSamePadConv2d(48, 48, 5, stride=2, image_size=24, freq_norm="ortho", groups=48, bias=False).cuda()
+    m = sfconv.SFSamePadConv2d(C, C, k, stride=stride, image_size=hw, freq_norm="ortho", groups=C, bias=False).cuda()
     with torch.no_grad():
         m.sf_coef.fill_(0.2)
     m = m.to(memory_format=torch.channels_last)
-    x = torch.randn(4, 48, 24, 24, device="cuda").contiguous(memory_format=torch.channels_last)
-    outs = []
-    for glue in (True, False):
-        sfconv.USE_GLUE_KERNELS = glue
-        xi = x.clone().requires_grad_()
-        m.zero_grad()
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            y = m(xi)
-        y.float().square().mean().backward()
-        outs.append((y.float(), xi.grad.float(), m.freq_conv.weight.grad.clone(), m.sf_coef.grad.clone()))
-    sfconv.USE_GLUE_KERNELS = True
-    for a, b in zip(*outs):
-        torch.testing.assert_close(a, b, rtol=3e-2, atol=3e-2 * float(b.abs().max()) + 1e-6)
+    x = torch.randn(4, C, hw, hw, device="cuda").contiguous(memory_format=torch.channels_last)
+    outs = {}
+    try:
+        for mode, (gemm, glue) in {"gemm": (True, True), "glue": (False, True), "plain": (False, False)}.items():
+            sfconv.USE_DFT_GEMM, sfconv.USE_GLUE_KERNELS = gemm, glue
+            xi = x.clone().requires_grad_()
+            m.zero_grad()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = m(xi)
+            y.float().square().mean().backward()
+            outs[mode] = (y.float(), xi.grad.float(), m.freq_conv.weight.grad.clone(), m.sf_coef.grad.clone().reshape(1),
+                          m.weight.grad.clone())
+    finally:
+        sfconv.USE_DFT_GEMM, sfconv.USE_GLUE_KERNELS = True, True
+    for mode in ("gemm", "glue"):
+        for a, b in zip(outs[mode], outs["plain"]):
+            torch.testing.assert_close(a, b, rtol=5e-2, atol=3e-2 * float(b.abs().max()) + 1e-6)
+
+
+def test_dft_gemm_matrices_fp32():
+    """The four DFT matrices reproduce rfft2+cat and tensor_split+complex+irfft2 exactly when run in fp32."""
+    from unidefense_b200.model import sfconv
+    for (h, w) in [(12, 12), (24, 24), (48, 48), (9, 7), (8, 6)]:
+        for norm in ("ortho", None):
+            N, C = 2, 6
+            wh = w // 2 + 1
+            L, R, Li, A = sfconv._dft_mats(h, w, norm, torch.device("cuda"))
+            x = torch.randn(N, C, h, w, device="cuda").contiguous(memory_format=torch.channels_last)
+            V = torch.matmul(L, x.permute(0, 2, 3, 1).reshape(N, h, w * C))
+            planar = torch.matmul(R, V.reshape(N * h, 2 * w, C)).reshape(N, h, wh, 2 * C).permute(0, 3, 1, 2)
+            f = torch.fft.rfft2(x, norm=norm)
+            want = torch.cat([f.real, f.imag], 1)
+            torch.testing.assert_close(planar, want, rtol=1e-4, atol=1e-5 * float(want.abs().max()))
+            Q = torch.randn(N, 2 * C, h, wh, device="cuda").contiguous(memory_format=torch.channels_last)
+            G = torch.matmul(Li, Q.permute(0, 2, 3, 1).reshape(N, h, wh * 2 * C))
+            y = torch.matmul(A, G.reshape(N * h, 4 * wh, C)).reshape(N, h, w, C).permute(0, 3, 1, 2)
+            re, im = torch.tensor_split(Q, 2, dim=1)
+            want = torch.fft.irfft2(torch.complex(re.contiguous(), im.contiguous()), s=(h, w), norm=norm)
+            torch.testing.assert_close(y, want, rtol=1e-4, atol=1e-5 * float(want.abs().max()))

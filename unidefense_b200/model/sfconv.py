@@ -25,9 +25,82 @@ import torch.nn.functional as F
 USE_GLUE_KERNELS = os.environ.get("UD_SFCONV_GLUE", "1") != "0"
 
 
+# Under bf16 autocast with channels-last activations (the benchmark configuration) the two small 2-D transforms are
+# evaluated as DFT-by-GEMM on the tensor cores: with x stored [N, h, w, C], rfft2 + cat([re, im]) is
+#     V = L @ x.view(N, h, w*C)            L [2h x h]   rows (j, ri):  cos / -sin of 2 pi j r / h
+#     P = R @ V.view(N*h, 2w, C)           R [2wh x 2w] rows (k, ri'), cols (ri, s): complex product with e^{-2 pi i k s / w}
+# and P viewed [N, h, wh, 2C] IS the channels-last planar spectrum the 1x1 convolution consumes; the inverse
+# (tensor_split + complex + irfft2, c2r semantics) is
+#     G = Li @ Q.view(N, h, wh*2C)         Li [2h x h]  rows (r, p): cos / sin of 2 pi j r / h
+#     y = A  @ G.view(N*h, 4wh, C)         A [w x 4wh]  folds the complex product and the Hermitian weights m_k
+# Four batched library GEMMs replace copy->fp32, R2C, C2C, pack, unpack, C2R and their backward twins; autograd
+# differentiates the matmuls.  Exact fp32 runs keep the cuFFT path (bf16 twiddles carry ~3 significant digits).
+USE_DFT_GEMM = os.environ.get("UD_SFCONV_DFT_GEMM", "1") != "0"
+_DFT_MAX = 64
+_dft_cache = {}
+
+
+def _dft_mats(h, w, norm, device):
+    key = (h, w, norm, str(device))
+    if key in _dft_cache:
+        return _dft_cache[key]
+    wh = w // 2 + 1
+    dd = torch.float64
+    fs = 1.0 / math.sqrt(h * w) if norm == "ortho" else 1.0            # forward scale
+    is_ = 1.0 / math.sqrt(h * w) if norm == "ortho" else 1.0 / (h * w)  # inverse scale
+    ah = 2 * math.pi * torch.outer(torch.arange(h, dtype=dd), torch.arange(h, dtype=dd)) / h      # [j, r]
+    aw = 2 * math.pi * torch.outer(torch.arange(wh, dtype=dd), torch.arange(w, dtype=dd)) / w     # [k, s]
+    ch, sh, cw, sw = torch.cos(ah), torch.sin(ah), torch.cos(aw), torch.sin(aw)
+    # forward, height: V[(j, ri), r]
+    L = torch.stack([ch, -sh], dim=1).reshape(2 * h, h)
+    # forward, width: P[(k, ri'), (ri, s)] : re' = cw*re + sw*im ; im' = -sw*re + cw*im
+    R = torch.stack([torch.cat([cw, sw], dim=1), torch.cat([-sw, cw], dim=1)], dim=1).reshape(2 * wh, 2 * w) * fs
+    # inverse, height: G[(r, p), j] : p=0 -> cos, p=1 -> sin   (e^{+i})
+    Li = torch.stack([ch.t(), sh.t()], dim=1).reshape(2 * h, h)
+    # inverse, width: y[s] = sum_k m_k (Tre cos - Tim sin), Tre = G0[ri0] - G1[ri1], Tim = G1[ri0] + G0[ri1]
+    m = torch.full((wh,), 2.0, dtype=dd)
+    m[0] = 1.0
+    if w % 2 == 0:
+        m[-1] = 1.0
+    cm, sm = (cw * m[:, None]).t(), (sw * m[:, None]).t()          # [s, k]
+    a0 = torch.stack([cm, -sm], dim=2).reshape(w, 2 * wh)          # cols (k, ri) acting on G0
+    a1 = torch.stack([-sm, -cm], dim=2).reshape(w, 2 * wh)         # cols (k, ri) acting on G1
+    A = torch.cat([a0, a1], dim=1) * is_                           # [w, (p, k, ri)]
+    mats = tuple(t.to(device=device, dtype=torch.float32) for t in (L, R, Li, A))
+    _dft_cache[key] = mats
+    return mats
+
+
+def _dft_gemm_ok(x, spat):
+    h, w = x.shape[-2:]
+    return (USE_DFT_GEMM and x.is_cuda and torch.is_autocast_enabled() and x.dim() == 4 and h <= _DFT_MAX and w <= _DFT_MAX
+            and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
+
+
+def _sf_forward_gemm(x, spat, freq_conv, sf_coef, norm):
+    N, C, h, w = x.shape
+    wh = w // 2 + 1
+    L, R, Li, A = _dft_mats(h, w, norm, x.device)
+    xl = x.permute(0, 2, 3, 1)                                        # [N, h, w, C] view of the channels-last storage
+    V = torch.matmul(L, xl.reshape(N, h, w * C))                      # [N, 2h, w*C]  = [n, j, ri, s, c]
+    P = torch.matmul(R, V.reshape(N * h, 2 * w, C))                   # [N*h, 2wh, C] = [n, j, k, ri', c]
+    planar = P.reshape(N, h, wh, 2 * C).permute(0, 3, 1, 2)           # channels-last [N, 2C, h, wh]
+    Q = freq_conv(planar)
+    Co = Q.shape[1] // 2
+    Ql = Q.permute(0, 2, 3, 1).reshape(N, h, wh * 2 * Co)             # [n, j, (k, ri, c)]
+    G = torch.matmul(Li, Ql)                                          # [N, 2h, ...]  = [n, r, p, k, ri, c]
+    y = torch.matmul(A, G.reshape(N * h, 4 * wh, Co))                 # [N*h, w, Co]
+    y = y.reshape(N, h, w, Co).permute(0, 3, 1, 2)                    # channels-last [N, Co, h, w]
+    if tuple(y.shape[-2:]) != tuple(spat.shape[-2:]):
+        y = F.adaptive_avg_pool2d(y, spat.shape[-2:])
+    return torch.lerp(spat, y.to(spat.dtype), torch.sigmoid(sf_coef).to(spat.dtype))
+
+
 def _sf_forward(x, spat, freq_conv, sf_coef, norm):
     """(1 - sigmoid(sf_coef)) * spat + sigmoid(sf_coef) * pool(irfft2(freq_conv(cat rfft2(x))))."""
     size = x.shape[-2:]
+    if _dft_gemm_ok(x, spat):
+        return _sf_forward_gemm(x, spat, freq_conv, sf_coef, norm)
     if USE_GLUE_KERNELS and x.is_cuda:
         from .. import ops
         xf = x.to(dtype=torch.float32, memory_format=torch.contiguous_format)
