@@ -147,14 +147,18 @@ def require_cuda_f32(*tensors):
 
 
 _ws = {}
+_ws_retired = []
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only byte workspace per (device, stream); safe because every kernel that uses it
-    is enqueued on that same stream."""
+    """Grow-only byte workspace per (device, stream); safe because every kernel that uses it is enqueued on
+    that same stream.  Superseded buffers are kept alive for the process lifetime: a captured CUDA graph may
+    still hold their addresses."""
     key = (device.index if device.index is not None else torch.cuda.current_device(), stream())
     t = _ws.get(key)
     if t is None or t.numel() < nbytes:
+        if t is not None:
+            _ws_retired.append(t)
         t = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _ws[key] = t
     return t

@@ -9,12 +9,12 @@
 //     gz = gy*act'(z); S1 = sum gz; S2 = sum gz*xh
 //     gx = gamma*rstd*(gz - S1/E - xh*S2/E); ggamma[c] = sum_n S2; gbeta[c] = sum_n S1
 //
-// Single-pass design: a plane (or a 1/CS slice of it) lives in REGISTERS -- 256 threads x up to 9
-// float4 -- so x is read from HBM exactly once and y written once (the algorithmic minimum,
-// 2E*4 B fwd / 3E*4 B bwd).  Planes too large for one CTA are split over a thread-block cluster
-// of CS in {2,4,8} CTAs that exchange their partial sums through distributed shared memory.
-// Two-pass statistics (mean, then centred second moment) from the registers, like ATen's
-// instance_norm, so no E[x^2]-E[x]^2 cancellation.
+// Single-pass design: a plane lives in REGISTERS, split over `nw` warps that each own a contiguous slab
+// (<= 9 float4 per lane forward, 5 + 5 backward), so x is read from HBM exactly once and y written once (the
+// algorithmic minimum, 2E*4 B fwd / 3E*4 B bwd).  nw <= 8: G = nw warps per plane, 8/G planes per CTA;
+// nw > 8: a thread-block cluster of nw/8 CTAs per plane exchanging partials through distributed shared memory.
+// Statistics are thread-local two-pass (mean, centred M2) merged with Chan's formula, so there is no
+// E[x^2]-E[x]^2 cancellation and only ONE cross-warp exchange per reduction.
 // The forward can also emit the per-plane mean of y (the triplet features dec_out.mean([-2,-1]),
 // model/unidefense.py:232-236) for free; the backward accepts its gradient.
 #include <cooperative_groups.h>
