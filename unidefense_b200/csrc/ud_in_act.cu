@@ -148,7 +148,7 @@ __device__ __forceinline__ float ia_fold_sum(const float (*slots)[K], int k, int
   return ud_warp_sum(v);
 }
 
-template <bool CLUSTER, int ACT>
+template <bool CLUSTER, int ACT, bool WANT_MEAN>
 __global__ void __launch_bounds__(IA_THREADS, 4)
 ia_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               float4* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
@@ -211,7 +211,7 @@ ia_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ gamma, con
       o.y = ia_act<ACT>(fmaf(v[i].y, a_, b_));
       o.z = ia_act<ACT>(fmaf(v[i].z, a_, b_));
       o.w = ia_act<ACT>(fmaf(v[i].w, a_, b_));
-      ys += (o.x + o.y) + (o.z + o.w);
+      if (WANT_MEAN) ys += (o.x + o.y) + (o.z + o.w);
       yp[idx] = o;
     }
   }
@@ -220,7 +220,7 @@ ia_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ gamma, con
     mean_out[ge.plane] = mu;
     rstd_out[ge.plane] = rstd;
   }
-  if (ymean_out != nullptr) {   // uniform across the grid
+  if (WANT_MEAN) {
     ys = ud_warp_sum(ys);
     const float ymine[1] = {ys};
     ia_exchange<CLUSTER, 1>(yslots, ymine, ge.rank, cs);
@@ -235,7 +235,7 @@ ia_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const
               const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd_in,
               const float* __restrict__ g_ymean, float4* __restrict__ gx, float* __restrict__ s1_out,
               float* __restrict__ s2_out, int planes, int C, int E4, int G, int cs, int vpt) {
-  __shared__ float slots[IA_MAX_CS * IA_WARPS][2];
+  __shared__ __align__(8) float slots[IA_MAX_CS * IA_WARPS][2];
   const IaGeom ge = ia_geom<CLUSTER>(planes, G, cs);
   const int lane = threadIdx.x & 31;
   const int per_w = (E4 + ge.nw - 1) / ge.nw;
@@ -284,8 +284,13 @@ ia_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const
   s2 = ud_warp_sum(s2);
   const float mine[2] = {s1, s2};
   ia_exchange<CLUSTER, 2>(slots, mine, ge.rank, cs);
-  const float S1 = ia_fold_sum<2>(slots, 0, ge.slot0, ge.nw);
-  const float S2 = ia_fold_sum<2>(slots, 1, ge.slot0, ge.nw);
+  // plain broadcast reads: measured faster here than a second shuffle tree (two dependent 5-step chains)
+  float S1 = 0.f, S2 = 0.f;
+  for (int i = 0; i < ge.nw; ++i) {
+    const float2 sv = *reinterpret_cast<const float2*>(&slots[ge.slot0 + i][0]);
+    S1 += sv.x;
+    S2 += sv.y;
+  }
   const float m1 = S1 * invE, m2 = S2 * invE, k = g * rstd;
 #pragma unroll
   for (int i = 0; i < IA_VMAX_BWD; ++i) {
@@ -451,11 +456,14 @@ extern "C" int ud_in_act_fwd(const float* x, const float* gamma, const float* be
   if (aligned && ia_pick(HW, IA_VMAX_FWD, &G, &cs, &vpt)) {
     const float4* x4 = reinterpret_cast<const float4*>(x);
     float4* y4 = reinterpret_cast<float4*>(y);
-    if (cs == 1)
-      IA_ACT_SWITCH(act, return ia_launch(ia_fwd_kernel<false, ACT_>, ud_cdiv(planes, IA_WARPS / G), 1, stream, x4, gamma,
-                                          beta, y4, mean, rstd, ymean, planes, C, HW / 4, G, cs, vpt, eps));
-    IA_ACT_SWITCH(act, return ia_launch(ia_fwd_kernel<true, ACT_>, planes * cs, cs, stream, x4, gamma, beta, y4, mean,
-                                        rstd, ymean, planes, C, HW / 4, G, cs, vpt, eps));
+#define IA_FWD(CL, WM, BLOCKS)                                                                                      \
+  IA_ACT_SWITCH(act, return ia_launch(ia_fwd_kernel<CL, ACT_, WM>, BLOCKS, cs, stream, x4, gamma, beta, y4, mean, rstd, \
+                                      ymean, planes, C, HW / 4, G, cs, vpt, eps))
+    if (cs == 1 && ymean) IA_FWD(false, true, ud_cdiv(planes, IA_WARPS / G));
+    if (cs == 1) IA_FWD(false, false, ud_cdiv(planes, IA_WARPS / G));
+    if (ymean) IA_FWD(true, true, planes * cs);
+    IA_FWD(true, false, planes * cs);
+#undef IA_FWD
   }
   ia_fwd_generic_kernel<<<planes, IA_THREADS, 0, stream>>>(x, gamma, beta, y, mean, rstd, ymean, C, HW, eps, act);
   return ud_check_launch("ia_fwd_generic");

@@ -13,10 +13,13 @@
 #define LS_MAX_N 128
 
 // ---------------------------------------------------------------- a9 triplet
-// one CTA; dynamic smem: dist [nr][N], H [nr][N], sq [N], gu [nr], fp [nr], fn [nr]
-__global__ void __launch_bounds__(256)
+// one CTA of 512 threads; dynamic smem: dist [N][N], H [N][N], sq [N], gu/fp/fn [N] each, then (when it fits)
+// a copy of feat [N][c].  The kernel is a chain of short dependent phases on one SM, so its time is load
+// latency: with the features staged in shared memory every phase reads at LDS latency instead of L2's.
+#define LS_TRI_THREADS 512
+__global__ void __launch_bounds__(LS_TRI_THREADS)
 ls_triplet_kernel(const float* __restrict__ feat, const long long* __restrict__ labels, float* __restrict__ loss,
-                  float* __restrict__ gfeat, int N, int c) {
+                  float* __restrict__ gfeat, int N, int c, int staged) {
   extern __shared__ float smf[];
   __shared__ int s_nr;
   __shared__ float red[33];
@@ -29,20 +32,31 @@ ls_triplet_kernel(const float* __restrict__ feat, const long long* __restrict__ 
     s_lab[i] = l;
     if (l == 0) atomicAdd(&s_nr, 1);  // N_real = #(labels == 0)   (triplet_loss.py:39)
   }
-  __syncthreads();
-  const int nr = s_nr;
   float* dist = smf;
   float* Hm = dist + N * N;
   float* sq = Hm + N * N;
   float* gu = sq + N;
   float* fpv = gu + N;
   float* fnv = fpv + N;
+  float* fstage = smf + ((2 * N * N + 4 * N + 3) & ~3);   // 16-byte aligned (host sizes it the same way)
+  if (staged) {
+    const int tot = N * c;
+    if ((c & 3) == 0 && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0)) {
+      for (int i = tid; i < tot / 4; i += nth)
+        reinterpret_cast<float4*>(fstage)[i] = __ldg(reinterpret_cast<const float4*>(feat) + i);
+    } else {
+      for (int i = tid; i < tot; i += nth) fstage[i] = __ldg(feat + i);
+    }
+  }
+  const float* f = staged ? fstage : feat;
+  __syncthreads();
+  const int nr = s_nr;
   // squared norms
   const int warp = tid >> 5, lane = tid & 31, nwarps = nth >> 5;
   for (int i = warp; i < N; i += nwarps) {
     float s = 0.f;
     for (int k = lane; k < c; k += 32) {
-      const float v = feat[(long long)i * c + k];
+      const float v = f[(long long)i * c + k];
       s = fmaf(v, v, s);
     }
     s = ud_warp_sum(s);
@@ -53,7 +67,7 @@ ls_triplet_kernel(const float* __restrict__ feat, const long long* __restrict__ 
   for (int p = warp; p < nr * N; p += nwarps) {
     const int i = p / N, j = p - i * N;
     float s = 0.f;
-    for (int k = lane; k < c; k += 32) s = fmaf(feat[(long long)i * c + k], feat[(long long)j * c + k], s);
+    for (int k = lane; k < c; k += 32) s = fmaf(f[(long long)i * c + k], f[(long long)j * c + k], s);
     s = ud_warp_sum(s);
     if (lane == 0) {
       const float q = sq[i] + sq[j] - 2.f * s;
@@ -87,17 +101,17 @@ ls_triplet_kernel(const float* __restrict__ feat, const long long* __restrict__ 
     const float u = fn - fp;
     // SoftMarginLoss(u, 1) = log(1 + exp(-u)); d/du = -sigmoid(-u)
     const float l = (u > 0.f) ? log1pf(expf(-u)) : (-u + log1pf(expf(u)));
+    const float gui = -1.f / (1.f + expf(u)) / (float)nr;
     if (lane == 0) {
       lsum += l;
       fpv[i] = fp;
       fnv[i] = fn;
-      gu[i] = -1.f / (1.f + expf(u)) / (float)nr;
+      gu[i] = gui;
     }
     // dL/dd_ij -> H_ij = (dL/dd_ij) / d_ij (masked by the clamp)
     for (int j = lane; j < N; j += 32) {
       const float d = dist[i * N + j];
       float g = 0.f;
-      const float gui = -1.f / (1.f + expf(u)) / (float)nr;
       if (s_lab[j] == li) {
         if (j != i) g = -gui * (expf(d) / (sp + eps)) * (1.f + d - fp);
       } else {
@@ -120,12 +134,12 @@ ls_triplet_kernel(const float* __restrict__ feat, const long long* __restrict__ 
     }
     rs = ud_warp_sum(rs);
     for (int k = lane; k < c; k += 32) {
-      float acc = feat[(long long)m * c + k] * rs;
+      float acc = f[(long long)m * c + k] * rs;
       for (int j = 0; j < N; ++j) {
         float h = 0.f;
         if (m < nr) h += Hm[m * N + j];
         if (j < nr) h += Hm[j * N + m];
-        acc = fmaf(-h, feat[(long long)j * c + k], acc);
+        acc = fmaf(-h, f[(long long)j * c + k], acc);
       }
       gfeat[(long long)m * c + k] = acc;
     }
@@ -137,10 +151,13 @@ extern "C" int ud_triplet_fwd(const float* feat, const long long* labels, float*
   UD_REQUIRE(N >= 1 && c >= 1, UD_ERR_INVALID, "triplet: bad shape N=%d c=%d", N, c);
   UD_REQUIRE(N <= LS_MAX_N, UD_ERR_UNSUPPORTED, "triplet: per-rank batch %d > %d unsupported", N, LS_MAX_N);
   UD_REQUIRE(feat && labels && loss, UD_ERR_INVALID, "triplet: null pointer");
-  const size_t smem = sizeof(float) * (2ull * N * N + 4ull * N);
+  const size_t base = sizeof(float) * (2ull * N * N + 4ull * N);
+  const size_t stage = ud_align_up(sizeof(float) * (size_t)N * c, 16);
+  const int staged = (ud_align_up(base, 16) + stage <= (200u << 10)) ? 1 : 0;
+  const size_t smem = staged ? ud_align_up(base, 16) + stage : base;
   if (smem > (48u << 10))
     UD_CUDA(cudaFuncSetAttribute(ls_triplet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ls_triplet_kernel<<<1, 256, smem, stream>>>(feat, labels, loss, gfeat, N, c);
+  ls_triplet_kernel<<<1, LS_TRI_THREADS, smem, stream>>>(feat, labels, loss, gfeat, N, c, staged);
   return ud_check_launch("triplet");
 }
 
