@@ -65,7 +65,8 @@ def test_vs_oracle(case, act, training):
     kind, N, C, h, w = case
     if training and N * h * w < 2:
         pytest.skip("batch statistics need more than one value per channel")
-    g = torch.Generator().manual_seed(hash(case) % 1000)
+    # deterministic seed (hash() of a tuple holding a str is salted per process)
+    g = torch.Generator().manual_seed(1000 * N + 10 * C + h + w + len(kind) + (7 if act == "relu" else 0) + int(training))
     cin, D, k = (2 * C, 6, 1) if kind == "freq" else (C, 3, 3)
     x = torch.randn(N, cin, h, w, generator=g)
     diff = torch.rand(N, D, h, w, generator=g)
@@ -86,6 +87,22 @@ def test_vs_oracle(case, act, training):
                                    rmean.double(), rvar.double())
     ((m64 * gm.double()).sum() + (o64 * go.double()).sum()).backward()
     close(mask, m64); close(out, o64)
+    # non-differentiable points: a pre-activation within fp32 noise of the ReLU kink, or two channels tying for the
+    # channel maximum, legitimately route the gradient differently in fp32 and fp64 -> only the forward is comparable
+    with torch.no_grad():
+        pre = F.conv2d(x.double(), w1.double(), None, 1, k // 2)
+        pre, _, _ = O.batch_norm(pre, gamma.double(), beta.double(), rmean.double(), rvar.double(), training)
+        post = O.activation(pre, act)
+        top2 = post.topk(min(2, post.shape[1]), dim=1).values
+        tie = False
+        if post.shape[1] > 1:
+            tmask = (top2[:, 0] - top2[:, 1]).abs() < 1e-5 * top2[:, 0].abs().clamp(min=1e-3)
+            if act == "relu":
+                tmask &= top2[:, 0] > 0          # a tie at relu's 0 carries no gradient either way
+            tie = bool(tmask.any())
+        kink = act == "relu" and bool((pre.abs() < 2e-6).any())
+    if tie or kink:
+        pytest.skip("input hits a non-differentiable point (relu kink / channel-max tie); forward checked")
     for a, b in zip(tc, t64):
         close(a.grad, b.grad, rtol=3e-4, atol=3e-5 * float(b.grad.abs().max()) + 1e-7)
 
