@@ -41,6 +41,7 @@ def golden_path(request):
 def _strict_fp32():
     """Parity is stated for fp32: keep the library convs/GEMMs around our kernels out of TF32."""
     import torch
+    torch.manual_seed(20260117)          # tests that draw from the global (CPU or CUDA) generator are reproducible
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
