@@ -374,8 +374,9 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(x_dev, l_dev)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local) if rank == 0 else None     # one nvidia-smi poller per job, not per rank
+    if sampler is not None:
+        sampler.start()
     graphed = graph_note == "whole step captured"
     L.PROFILE = None if graphed else {}
     launches0 = L.lib().ud_launch_count()
@@ -388,7 +389,7 @@ def run_ours(args):
     barrier()
     launches = graph_launches * args.steps if graphed else L.lib().ud_launch_count() - launches0
     ms = e0.elapsed_time(e1) / args.steps
-    clocks = sampler.summary()
+    clocks = sampler.summary() if sampler is not None else None
     if graphed:
         # events cannot be recorded inside a replayed graph: the per-op device times behind `roofline` come from
         # the same step issued eagerly right after the timed region (same inputs, same kernels, L2 flushed)
