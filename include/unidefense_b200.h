@@ -16,6 +16,10 @@
  *  - return 0 on success, a negative UD_ERR_* code otherwise; ud_last_error() returns a
  *    thread-local message.  No exceptions cross this boundary.
  *  - workspaces are passed in by the caller; *_workspace_bytes() say how large.
+ *  - the first call for a new FFT length / resize pair builds its table with cudaMalloc + a synchronous copy:
+ *    warm every shape up once before capturing calls into a CUDA graph (all later calls are capture-safe).
+ *  - reductions are fixed-order (bitwise reproducible) except ud_recon_tail_bwd and ud_bilinear_ac_bwd, whose
+ *    transposed resize accumulates with float atomics.
  */
 #ifndef UNIDEFENSE_B200_H
 #define UNIDEFENSE_B200_H

@@ -91,7 +91,13 @@ def lib():
 # Optional per-op device timing (bench.py's roofline leg): when PROFILE is a dict, every C-ABI call that
 # passes through check() is bracketed by CUDA events on the launching stream: name -> [(start, end), ...].
 PROFILE = None
-_pending = []
+_tls = threading.local()       # start events are per thread: backward runs on autograd's worker thread
+
+
+def _pending():
+    if not hasattr(_tls, "pending"):
+        _tls.pending = []
+    return _tls.pending
 
 
 def _timed(fn):
@@ -100,14 +106,14 @@ def _timed(fn):
         if PROFILE is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record(torch.cuda.current_stream())
-            _pending.append(ev)
+            _pending().append(ev)
         return fn(*args)
     return call
 
 
 def check(rc: int, what: str = ""):
-    if PROFILE is not None and _pending:
-        ev0 = _pending.pop()
+    if PROFILE is not None and _pending():
+        ev0 = _pending().pop()
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record(torch.cuda.current_stream())
         PROFILE.setdefault(what, []).append((ev0, ev1))
