@@ -7,10 +7,12 @@
     python bench.py --impl reference --steps 3 --warmup 1             # reference arm: CPU port on the host cores
 
 A "step" is one training step of the drop-in UniDefenseModelEb4 (EfficientNet-B4, 380x380, per-GPU
-batch 32, bf16 autocast for the stock-torch backbone and dense convs, fp32 hot-path kernels) on synthetic
-face tensors: forward, the engine's first-pass loss (engine/abstract_engine.py:215-267), backward
-(+ NCCL gradient all-reduce under DDP, SyncBatchNorm as the engines wrap it) and the AdamW(amsgrad)
-update of the config template.  Rank 0 prints ONE JSON line (see README / DESIGN.md for the keys).
+batch 32, bf16 autocast + channels_last for the stock-torch backbone and dense convs, fp32 hot-path kernels)
+on synthetic face tensors: forward, the engine's first-pass loss (engine/abstract_engine.py:215-267), backward
+(+ NCCL gradient all-reduce under DDP, SyncBatchNorm as the engines wrap it -- by default the host-sync-free
+equivalent of unidefense_b200/parallel.py, `--syncbn torch` for the stock class) and the AdamW(amsgrad) update
+of the config template.  On one GPU the whole step is captured once and replayed as a CUDA graph (`--graph off`
+for eager launches).  Rank 0 prints ONE JSON line (see README / DESIGN.md §5 for the keys).
 """
 import argparse
 import json
