@@ -133,6 +133,24 @@ UD_API int ud_bn_bwd_reduce(const float* dz, const float* x, const float* mean, 
 UD_API int ud_bn_bwd_apply(const float* dz, const float* x, const float* mean, const float* rstd,
                            const float* gamma, const float* sum_dz, const float* sum_dz_xh, float inv_count,
                            float* gx, int N, int C, int HW, cudaStream_t stream);
+/* The dense projection itself -- FrequencyDynamicFilter.layer1[0] = nn.Conv2d(2C,2C,1) (model/modules.py:82-85),
+ * SpatialDynamicFilter.layer1[0] = nn.Conv2d(C,C,3,1,1) (model/modules.py:111-114), bias-free -- as ONE implicit
+ * GEMM on the 5th-generation tensor cores (TMA -> 128B-swizzled smem -> tcgen05.mma.kind::tf32 -> TMEM), with the
+ * BatchNorm2d batch statistics of layer1[1] produced per M tile in the epilogue.
+ *   x_hi [N,H,W,Cin] channels-last fp32 activations, w_hi [Cout, ksize*ksize, Cin] (tap = ky*ksize+kx);
+ *   x_lo / w_lo: nullable low parts for "3xTF32" (hi = TF32-rounded value, lo = x - hi): fp32-grade accuracy;
+ *   with both NULL the product is plain TF32 (what cuDNN computes under torch's default allow_tf32=True).
+ *   y [N,Cout,H,W] (NCHW); part_mean/part_m2 [m_tiles, Cout] and part_cnt [m_tiles] (all three or none):
+ *   per-tile mean, sum (x-mean)^2 and pixel count, merged by ud_bn_merge_partials into ud_bn_stats' outputs.
+ * Cin % 4 == 0, Cin >= 32, W <= 128.  ud_proj_prep_x / _w build the operand layouts (transpose + split).   */
+UD_API int ud_proj_m_tiles(int N, int H, int W, int ksize);
+UD_API int ud_proj_prep_x(const float* x_nchw, float* hi, float* lo, int N, int C, int P, cudaStream_t stream);
+UD_API int ud_proj_prep_w(const float* w, float* hi, float* lo, int Cout, int Cin, int taps, cudaStream_t stream);
+UD_API int ud_proj_fwd(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, float* y,
+                       float* part_mean, float* part_m2, float* part_cnt, int N, int H, int W, int Cin, int Cout,
+                       int ksize, cudaStream_t stream);
+UD_API int ud_bn_merge_partials(const float* part_mean, const float* part_m2, const float* part_cnt, float* mean,
+                                float* m2, int tiles, int C, cudaStream_t stream);
 /* Everything after layer1's conv: BN-apply + act + channel mean/max + cat(diff) + conv1x1 (w2 [2+D]) +
  * sigmoid -> mask [N,HW]; out [N,Cx,HW] = mask*x (nullable).  proj [N,Cp,HW] is the raw conv output.
  * pmean/pmax [N,HW] and argmax [N,HW] (first index on ties, like torch.max) are saved for backward.   */

@@ -31,6 +31,12 @@ def golden_ops():
     return torch.load(os.path.join(GOLDEN, "ops.pt"), weights_only=False)
 
 
+@pytest.fixture(scope="session")
+def golden_ops_r2():
+    import torch
+    return torch.load(os.path.join(GOLDEN, "ops_r2.pt"), weights_only=False)
+
+
 @pytest.fixture(scope="session", params=["eb4", "r18", "r50"])
 def golden_path(request):
     import torch

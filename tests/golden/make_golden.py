@@ -197,6 +197,47 @@ def make_ops(ref):
 
 
 # --------------------------------------------------------------------------------------
+def dyfi_case(ref, kind, C, h, w, act, N):
+    """One FrequencyDynamicFilter / SpatialDynamicFilter run of the reference (model/modules.py:79-134)."""
+    M = ref.modules
+    A = ref.efficientnet.MemoryEfficientSwish if act == "swish" else nn.ReLU
+    if kind == "freq":
+        mod = M.FrequencyDynamicFilter(C, A, nn.BatchNorm2d, True, False)
+        cin, cd = 2 * C, 6
+    else:
+        mod = M.SpatialDynamicFilter(C, A, nn.BatchNorm2d, True, False)
+        cin, cd = C, 3
+    tag = f"dyfi_{kind}_{C}_{act}"
+    P.fill_state_dict_(mod, salt=1)
+    sd0 = {k: v.clone() for k, v in mod.state_dict().items()}
+    x = T(tag + "_x", (N, cin, h, w), "normal").requires_grad_()
+    diff = T(tag + "_d", (N, cd, h, w), "unit").abs()
+    mod.train()
+    o = mod(x, diff)
+    gm = T(tag + "_gm", o["mask"].shape, "normal")
+    go = T(tag + "_go", o["out"].shape, "normal")
+    params = [mod.layer1[0].weight, mod.layer1[1].weight, mod.layer1[1].bias, mod.layer2[0].weight]
+    gs = grads_of((o["mask"] * gm).sum() + (o["out"] * go).sum(), [x] + params)
+    sd1 = {k: v.clone() for k, v in mod.state_dict().items()}
+    mod.eval()
+    with torch.no_grad():
+        oe = mod(x, diff)
+    return {"kind": kind, "C": C, "act": act, "x": x.detach(), "diff": diff, "sd0": sd0, "sd1": sd1,
+            "mask": o["mask"].detach(), "out": o["out"].detach(), "gm": gm, "go": go,
+            "gx": gs[0], "gw1": gs[1], "ggamma": gs[2], "gbeta": gs[3], "gw2": gs[4],
+            "mask_eval": oe["mask"], "out_eval": oe["out"]}
+
+
+def make_ops_r2(ref):
+    """Round-2 additions (own file so ops.pt stays byte-identical): dynamic filters wide enough (>= 32 input
+    channels) to run their projection on the tcgen05 implicit-GEMM kernel."""
+    out = {}
+    out["dyfi_wide"] = [dyfi_case(ref, "freq", 32, 5, 3, "swish", 3), dyfi_case(ref, "freq", 18, 4, 3, "relu", 2),
+                        dyfi_case(ref, "spat", 48, 6, 6, "swish", 3), dyfi_case(ref, "spat", 36, 4, 5, "relu", 2)]
+    return out
+
+
+# --------------------------------------------------------------------------------------
 def make_path(ref, arch):
     """Run the reference MODEL CLASS in train mode (dropout off) and capture every tensor that
     crosses the hot-path boundary, plus gradients of a fixed hot-path loss."""
@@ -346,9 +387,100 @@ def make_full(ref, arch):
     return fix
 
 
+# --------------------------------------------------------------------------------------
+ENGINE_CFG = {"lambda_mask": 0.1, "lambda_triplet": 0.1, "lambda_recons": 0.1, "lambda_freq": 1.0, "lambda_fac": 0.1}
+ENGINE_OPT = dict(lr=1e-4, weight_decay=5e-6, amsgrad=True)      # config_template/forgery/model_udr18.yml
+ENGINE_NUM_STEPS = 10            # step 1: mask-mean branch, step 2: KL branch (cur_step > 0.1 * num_steps)
+
+
+def engine_param_groups(model, wd):
+    """timm.optim.optim_factory.param_groups_weight_decay as the engines use it (forgery_engine.py:152)."""
+    decay, no_decay = [], []
+    for n_, p_ in model.named_parameters():
+        if not p_.requires_grad:
+            continue
+        (no_decay if p_.ndim <= 1 or n_.endswith(".bias") else decay).append(p_)
+    return [{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": wd}]
+
+
+def engine_seed_for(want, sum_real, sum_fake):
+    """Smallest CPU-generator seed for which the pass-2 augmentation dispatch (model/unidefense.py:177-198, after
+    the two randperm calls of abstract_engine.py:288-289) takes the deterministic branch `want`
+    ('blur' = PERT_FUNCS[1], 'downscale' = PERT_FUNCS[2])."""
+    idx = {"noise": 0, "blur": 1, "downscale": 2}[want]
+    for seed in range(1, 10000):
+        torch.manual_seed(seed)
+        torch.randperm(sum_real)
+        torch.randperm(sum_fake)
+        if torch.rand(1) > 0.5:
+            continue
+        if int(torch.randint(0, 3, size=(1,))) == idx:
+            return seed
+    raise RuntimeError("no seed found")
+
+
+def make_engine(ref):
+    """Drive the reference's OWN AbstractEngine.train_unidefense_model (engine/abstract_engine.py:207-381),
+    unmodified, for two iterations on UDR18 (CPU, 1-rank gloo group; SURVEY App. C recipe): both passes, the
+    mask-mean branch (step 1) and the KL branch (step 2), fac loss, AdamW(amsgrad) + StepLR.  Dropout is off
+    (drop_rate 0, the hard-coded F.dropout(0.2) patched to identity) and the CPU generator is seeded per step so
+    that the perturbation dispatch picks blur (step 1) / downscale (step 2): deterministic, device-independent."""
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from torch.cuda.amp import GradScaler
+    Engine = ref_loader.load_abstract_engine()
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    R, N = 64, 4
+    model = ref.unidefense.UniDefenseModelRes18(drop_rate=0.0)
+    P.fill_state_dict_(model, salt=7)
+    model.train()
+
+    class E(Engine):
+        def __init__(self):
+            pass
+
+    eng = E()
+    eng.model, eng.device = model, torch.device("cpu")
+    eng.loss_criterion = {"softmax": ref.loss.LOSSES["cross_entropy"], "triplet": ref.loss.LOSSES["aw_triplet"],
+                          "kl_div": ref.loss.LOSSES["kl_div"], "fac": ref.loss.LOSSES["factorization"]}
+    eng.config = {"config": dict(ENGINE_CFG)}
+    eng.optimizer = torch.optim.AdamW(engine_param_groups(model, ENGINE_OPT["weight_decay"]), lr=ENGINE_OPT["lr"],
+                                      amsgrad=ENGINE_OPT["amsgrad"])
+    eng.scheduler = torch.optim.lr_scheduler.StepLR(eng.optimizer, step_size=5, gamma=0.5)
+    eng.warmup_step, eng.num_steps = 0, ENGINE_NUM_STEPS
+    scaler = GradScaler(2 ** 10)
+    x = T("engine_x_r18", (N, 3, R, R))
+    labels = torch.tensor([0] * (N // 2) + [1] * (N // 2))
+    seeds = [engine_seed_for("blur", N // 2, N // 2), engine_seed_for("downscale", N // 2, N // 2)]
+    steps = []
+    orig_dropout = F.dropout
+    F.dropout = lambda t, p=0.5, training=True, inplace=False: t * 1.0
+    try:
+        for i, seed in enumerate(seeds):
+            torch.manual_seed(seed)
+            ret = eng.train_unidefense_model(x, labels, i + 1, scaler, N // 2, N // 2)
+            losses = {k: float(v) for k, v in ret.items() if k != "cls_out"}
+            wn = {}
+            for n_, p_ in model.named_parameters():
+                idx = P.sample_indices(p_.numel(), 8, n_)
+                wn[n_] = {"norm": p_.detach().norm().item(), "sample": p_.detach().flatten()[idx].clone()}
+            bn = {k: v.clone() for k, v in model.state_dict().items()
+                  if k.startswith(("bottleneck.running", "freq_filter.layer1.1.running", "spat_filter.layer1.1.running"))}
+            steps.append({"seed": seed, "losses": losses, "cls_out": ret["cls_out"].detach().clone(), "weights": wn,
+                          "bn": bn, "lr": eng.optimizer.param_groups[0]["lr"]})
+    finally:
+        F.dropout = orig_dropout
+    return {"arch": "r18", "R": R, "N": N, "x": x, "labels": labels, "cfg": dict(ENGINE_CFG), "opt": dict(ENGINE_OPT),
+            "num_steps": ENGINE_NUM_STEPS, "sched": {"step_size": 5, "gamma": 0.5}, "steps": steps,
+            "pert": ["blur", "downscale"]}
+
+
 def main():
     ref = ref_loader.load()
-    which = sys.argv[1:] or ["ops", "eb4", "r18", "r50", "full"]
+    which = sys.argv[1:] or ["ops", "ops_r2", "eb4", "r18", "r50", "full", "engine"]
     if "full" in which:
         for arch in ("eb4", "r18", "r50"):
             fn = os.path.join(HERE, f"full_{arch}.pt")
@@ -357,6 +489,13 @@ def main():
     if "ops" in which:
         torch.save(make_ops(ref), os.path.join(HERE, "ops.pt"))
         print("wrote ops.pt", os.path.getsize(os.path.join(HERE, "ops.pt")))
+    if "engine" in which:
+        fn = os.path.join(HERE, "engine_r18.pt")
+        torch.save(make_engine(ref), fn)
+        print("wrote", fn, os.path.getsize(fn))
+    if "ops_r2" in which:
+        torch.save(make_ops_r2(ref), os.path.join(HERE, "ops_r2.pt"))
+        print("wrote ops_r2.pt", os.path.getsize(os.path.join(HERE, "ops_r2.pt")))
     for arch in ("eb4", "r18", "r50"):
         if arch in which:
             fn = os.path.join(HERE, f"path_{arch}.pt")

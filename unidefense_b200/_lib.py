@@ -46,6 +46,11 @@ SIGNATURES = {
     "ud_bn_stats": (c_i, [c_p] * 3 + [c_i] * 3 + [c_p]),
     "ud_bn_bwd_reduce": (c_i, [c_p] * 6 + [c_i] * 3 + [c_p]),
     "ud_bn_bwd_apply": (c_i, [c_p] * 7 + [c_f, c_p] + [c_i] * 3 + [c_p]),
+    "ud_proj_m_tiles": (c_i, [c_i] * 4),
+    "ud_proj_prep_x": (c_i, [c_p] * 3 + [c_i] * 3 + [c_p]),
+    "ud_proj_prep_w": (c_i, [c_p] * 3 + [c_i] * 3 + [c_p]),
+    "ud_proj_fwd": (c_i, [c_p] * 8 + [c_i] * 6 + [c_p]),
+    "ud_bn_merge_partials": (c_i, [c_p] * 5 + [c_i] * 2 + [c_p]),
     "ud_dyfi_mask_fwd": (c_i, [c_p] * 13 + [c_i] * 6 + [c_p]),
     "ud_dyfi_mask_bwd_workspace_bytes": (c_sz, [c_i, c_i]),
     "ud_dyfi_mask_bwd": (c_i, [c_p] * 18 + [c_sz] + [c_i] * 6 + [c_p]),

@@ -13,6 +13,8 @@ nn.Conv2d / nn.BatchNorm2d / nn.InstanceNorm2d child as the parameter holder so 
 SyncBatchNorm.convert_sync_batchnorm, DDP, weight-decay grouping and strict state_dict loading
 (engine/forgery_engine.py:142-154,:208) see the same tree as with the reference.
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -123,7 +125,7 @@ def merge_bn_stats(means, m2s, counts):
     return mean, m2, n
 
 
-def bn_forward_stats(bn, proj):
+def bn_forward_stats(bn, proj, local=None):
     """-> (mean [C], rstd [C], count, stat_reduce); `count` is a python float locally and a 0-dim DEVICE tensor
     under SyncBatchNorm (no host sync, CUDA-graph capturable).  Training: batch statistics (merged over ranks
     when `bn` is a SyncBatchNorm inside an initialised process group, engine/forgery_engine.py:142)
@@ -132,7 +134,7 @@ def bn_forward_stats(bn, proj):
     if not use_batch:
         return bn.running_mean, torch.rsqrt(bn.running_var + bn.eps), 0, None
     N, C, h, w = proj.shape
-    mean, m2 = ops.bn_local_stats(proj.detach())
+    mean, m2 = local if local is not None else ops.bn_local_stats(proj.detach())   # local: from the GEMM epilogue
     count = float(N * h * w)
     group = _sync_group(bn)
     reduce_fn = None
@@ -159,12 +161,23 @@ def bn_forward_stats(bn, proj):
     return mean, torch.rsqrt(var + bn.eps), (count if torch.is_tensor(count) else int(count)), reduce_fn
 
 
+# "tcgen05": our implicit-GEMM kernel (csrc/ud_proj.cu); "cudnn": the library convolution (A/B timing, UD_PROJ=cudnn)
+PROJ_BACKEND = os.environ.get("UD_PROJ", "tcgen05")
+
+
 class _DynamicFilter(nn.Module):
     def _mask(self, x, diff, want_out):
         conv, bn, act = self.layer1[0], self.layer1[1], self.layer1[2]
         x = x.float()
-        proj = conv(x).float()
-        mean, rstd, count, reduce_fn = bn_forward_stats(bn, proj)
+        use_batch = bn.training or bn.running_mean is None
+        local = None
+        if PROJ_BACKEND == "tcgen05" and ops.proj_supported(x, conv):
+            # layer1[0] on the tensor cores (tcgen05 implicit GEMM); its epilogue already holds the batch statistics
+            proj, pm, p2 = ops.proj_conv(x, conv.weight, want_stats=use_batch)
+            local = (pm, p2) if use_batch else None
+        else:
+            proj = conv(x).float()
+        mean, rstd, count, reduce_fn = bn_forward_stats(bn, proj, local)
         w2 = self.layer2[0].weight.reshape(-1)
         if self.layer2[0].bias is not None:      # bias=True: a constant-one guide channel carries it
             diff = torch.cat([diff, torch.ones_like(diff[:, :1])], dim=1)

@@ -289,6 +289,90 @@ def bn_local_stats(proj):
     return mean, m2
 
 
+def proj_precision():
+    """Arithmetic of the tcgen05 projections: plain TF32 when torch would let cuDNN use TF32 for convolutions
+    (torch's default), otherwise 3xTF32 (hi/lo operand split, fp32-grade accuracy)."""
+    return "tf32" if torch.backends.cudnn.allow_tf32 else "3xtf32"
+
+
+def proj_supported(x, conv):
+    """Shapes the tcgen05 implicit GEMM takes (include/unidefense_b200.h: ud_proj_fwd); anything else stays on
+    the library convolution."""
+    k = conv.kernel_size
+    return (x.is_cuda and x.dim() == 4 and conv.bias is None and conv.groups == 1 and k[0] == k[1] and k[0] in (1, 3)
+            and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) == (1, 1)
+            and tuple(conv.padding) == (k[0] // 2, k[0] // 2) and conv.padding_mode == "zeros"
+            and conv.in_channels % 4 == 0 and conv.in_channels >= 32 and x.shape[-1] <= 128)
+
+
+class _ProjConv(torch.autograd.Function):
+    """Bias-free 1x1 / 3x3 (pad 1) convolution = FrequencyDynamicFilter.layer1[0] / SpatialDynamicFilter.layer1[0]
+    (model/modules.py:82-85, :111-114) on tcgen05, returning the BatchNorm batch statistics of its output
+    (mean [Cout], m2 [Cout]) from the GEMM epilogue.  Backward: the library's convolution_backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, precision, want_stats):
+        L.require_cuda_f32(weight)
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise RuntimeError("proj_conv: x must be a CUDA fp32 tensor (no CPU fallback)")
+        N, Cin, H, W = x.shape
+        Cout, _, k, _ = weight.shape
+        lib = L.lib()
+        dev = x.device
+        split = precision == "3xtf32"
+        if precision not in ("tf32", "3xtf32"):
+            raise ValueError(f"proj_conv: precision {precision!r} (tf32 | 3xtf32)")
+        nhwc = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        if nhwc and not split:
+            x_hi, x_lo = x, None                       # already [N,H,W,C] in memory
+        else:
+            xc = x.contiguous()
+            x_hi = torch.empty(N, H, W, Cin, device=dev, dtype=torch.float32)
+            x_lo = torch.empty_like(x_hi) if split else None
+            L.check(lib.ud_proj_prep_x(L.ptr(xc), L.ptr(x_hi), L.ptr(x_lo), N, Cin, H * W, L.stream()), "proj_prep_x")
+        wc = weight.contiguous()
+        if k == 1 and not split:
+            w_hi, w_lo = wc, None
+        else:
+            w_hi = torch.empty(Cout, k * k, Cin, device=dev, dtype=torch.float32)
+            w_lo = torch.empty_like(w_hi) if split else None
+            L.check(lib.ud_proj_prep_w(L.ptr(wc), L.ptr(w_hi), L.ptr(w_lo), Cout, Cin, k * k, L.stream()), "proj_prep_w")
+        y = torch.empty(N, Cout, H, W, device=dev, dtype=torch.float32)
+        tiles = lib.ud_proj_m_tiles(N, H, W, k)
+        if tiles < 0:
+            raise RuntimeError("proj_conv: " + lib.ud_last_error().decode(errors="replace"))
+        pm = p2 = pc = mean = m2 = None
+        if want_stats:
+            pm = torch.empty(tiles, Cout, device=dev, dtype=torch.float32)
+            p2 = torch.empty_like(pm)
+            pc = torch.empty(tiles, device=dev, dtype=torch.float32)
+        L.check(lib.ud_proj_fwd(L.ptr(x_hi), L.ptr(x_lo), L.ptr(w_hi), L.ptr(w_lo), L.ptr(y), L.ptr(pm), L.ptr(p2),
+                                L.ptr(pc), N, H, W, Cin, Cout, k, L.stream()), "proj_fwd")
+        if want_stats:
+            mean = torch.empty(Cout, device=dev, dtype=torch.float32)
+            m2 = torch.empty_like(mean)
+            L.check(lib.ud_bn_merge_partials(L.ptr(pm), L.ptr(p2), L.ptr(pc), L.ptr(mean), L.ptr(m2), tiles, Cout,
+                                             L.stream()), "bn_merge_partials")
+            ctx.mark_non_differentiable(mean, m2)
+        ctx.save_for_backward(x, weight)
+        ctx.k = k
+        return y, mean, m2
+
+    @staticmethod
+    def backward(ctx, gy, _gm, _g2):
+        x, weight = ctx.saved_tensors
+        k = ctx.k
+        gx, gw, _ = torch.ops.aten.convolution_backward(
+            gy.contiguous(), x, weight, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
+            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        return gx, gw, None, None
+
+
+def proj_conv(x, weight, precision=None, want_stats=True):
+    """-> (y [N,Cout,H,W] NCHW fp32, mean [Cout] | None, m2 [Cout] | None)."""
+    return _ProjConv.apply(x, weight, precision or proj_precision(), bool(want_stats))
+
+
 class _DyfiMask(torch.autograd.Function):
     """BN-apply + act + channel mean/max + cat(diff) + conv1x1 + sigmoid (+ mask*x)
     (model/modules.py:94-104, :123-133).  mean/rstd are the (possibly cross-rank) BN statistics;
