@@ -421,18 +421,45 @@ def engine_seed_for(want, sum_real, sum_fake):
 
 def make_engine(ref):
     """Drive the reference's OWN AbstractEngine.train_unidefense_model (engine/abstract_engine.py:207-381),
-    unmodified, for two iterations on UDR18 (CPU, 1-rank gloo group; SURVEY App. C recipe): both passes, the
-    mask-mean branch (step 1) and the KL branch (step 2), fac loss, AdamW(amsgrad) + StepLR.  Dropout is off
-    (drop_rate 0, the hard-coded F.dropout(0.2) patched to identity) and the CPU generator is seeded per step so
-    that the perturbation dispatch picks blur (step 1) / downscale (step 2): deterministic, device-independent."""
+    unmodified, on UDR18 (CPU, 1-rank gloo group; SURVEY App. C recipe): both passes, fac loss, GradScaler, scheduler.
+      run "adamw": ONE iteration with the template optimizer (AdamW amsgrad, forgery/model_udr18.yml) -- mask-mean
+                   branch, `blur` perturbation.  (AdamW's first update is lr*g/|g| per weight: a second iteration
+                   would amplify any 1e-7 gradient difference of near-zero-gradient weights chaotically, which says
+                   nothing about the model under test, so the multi-iteration run uses the registry's SGD.)
+      run "sgd":   TWO iterations with optimizer 'sgd' (optimizer/__init__.py:11, momentum 0.9): iteration 1 =
+                   mask-mean branch + `blur`, iteration 2 = KL mask-alignment branch (cur_step > 0.1*num_steps)
+                   + `downscale`, weights already moved by two updates.
+    Dropout is off (drop_rate 0, the hard-coded F.dropout(0.2) patched to identity) and the CPU generator is seeded
+    per iteration so that the perturbation dispatch is deterministic and device-independent."""
     import torch.distributed as dist
-    import torch.nn.functional as F
-    from torch.cuda.amp import GradScaler
     Engine = ref_loader.load_abstract_engine()
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29533")
         dist.init_process_group("gloo", rank=0, world_size=1)
+    out = {"arch": "r18", "R": 64, "N": 4, "cfg": dict(ENGINE_CFG), "num_steps": ENGINE_NUM_STEPS,
+           "sched": {"step_size": 5, "gamma": 0.5}, "runs": {}}
+    for name, opt, n in (("adamw", dict(name="adamw", **ENGINE_OPT), 1),
+                         ("sgd", dict(name="sgd", lr=3e-4, momentum=0.9, weight_decay=5e-6), 2)):
+        fix, alt = _engine_run(ref, Engine, 0.0, opt, n), _engine_run(ref, Engine, 2e-7, opt, n)
+        # the reference's own sensitivity to a one-ulp input perturbation (train-mode BatchNorm on 4 samples, |.|
+        # kinks): the parity test scales its tolerances with it
+        fix["noise"] = [{"losses": {k: abs(a["losses"][k] - b["losses"][k]) for k in a["losses"]},
+                         "cls_out": float((a["cls_out"] - b["cls_out"]).abs().max()),
+                         "weight_norm_rel": {k: abs(v["norm"] - b["weights"][k]["norm"]) / (v["norm"] + 1e-30)
+                                             for k, v in a["weights"].items()},
+                         "weight_sample": {k: float((v["sample"] - b["weights"][k]["sample"]).abs().max())
+                                           for k, v in a["weights"].items()}}
+                        for a, b in zip(fix["steps"], alt["steps"])]
+        fix["opt"] = opt
+        out["runs"][name] = fix
+        out["x"], out["labels"] = fix.pop("x"), fix.pop("labels")
+    return out
+
+
+def _engine_run(ref, Engine, eps, opt, n_steps):
+    import torch.nn.functional as F
+    from torch.cuda.amp import GradScaler
     R, N = 64, 4
     model = ref.unidefense.UniDefenseModelRes18(drop_rate=0.0)
     P.fill_state_dict_(model, salt=7)
@@ -447,14 +474,18 @@ def make_engine(ref):
     eng.loss_criterion = {"softmax": ref.loss.LOSSES["cross_entropy"], "triplet": ref.loss.LOSSES["aw_triplet"],
                           "kl_div": ref.loss.LOSSES["kl_div"], "fac": ref.loss.LOSSES["factorization"]}
     eng.config = {"config": dict(ENGINE_CFG)}
-    eng.optimizer = torch.optim.AdamW(engine_param_groups(model, ENGINE_OPT["weight_decay"]), lr=ENGINE_OPT["lr"],
-                                      amsgrad=ENGINE_OPT["amsgrad"])
+    kw = {k: v for k, v in opt.items() if k not in ("name", "weight_decay")}
+    cls = {"adamw": torch.optim.AdamW, "sgd": torch.optim.SGD}[opt["name"]]       # optimizer/__init__.py:10-19
+    eng.optimizer = cls(engine_param_groups(model, opt["weight_decay"]), **kw)
     eng.scheduler = torch.optim.lr_scheduler.StepLR(eng.optimizer, step_size=5, gamma=0.5)
     eng.warmup_step, eng.num_steps = 0, ENGINE_NUM_STEPS
     scaler = GradScaler(2 ** 10)
     x = T("engine_x_r18", (N, 3, R, R))
+    x_clean = x
+    if eps:
+        x = x + eps * torch.randn(x.shape, generator=torch.Generator().manual_seed(1))
     labels = torch.tensor([0] * (N // 2) + [1] * (N // 2))
-    seeds = [engine_seed_for("blur", N // 2, N // 2), engine_seed_for("downscale", N // 2, N // 2)]
+    seeds = [engine_seed_for("blur", N // 2, N // 2), engine_seed_for("downscale", N // 2, N // 2)][:n_steps]
     steps = []
     orig_dropout = F.dropout
     F.dropout = lambda t, p=0.5, training=True, inplace=False: t * 1.0
@@ -473,9 +504,7 @@ def make_engine(ref):
                           "bn": bn, "lr": eng.optimizer.param_groups[0]["lr"]})
     finally:
         F.dropout = orig_dropout
-    return {"arch": "r18", "R": R, "N": N, "x": x, "labels": labels, "cfg": dict(ENGINE_CFG), "opt": dict(ENGINE_OPT),
-            "num_steps": ENGINE_NUM_STEPS, "sched": {"step_size": 5, "gamma": 0.5}, "steps": steps,
-            "pert": ["blur", "downscale"]}
+    return {"x": x_clean, "labels": labels, "steps": steps, "pert": ["blur", "downscale"][:n_steps]}
 
 
 def main():

@@ -35,6 +35,10 @@
 #define PJ_A_BYTES (PJ_BLOCK_M * PJ_BLOCK_K * 4)
 #define PJ_B_BYTES (PJ_BLOCK_N * PJ_BLOCK_K * 4)
 #define PJ_TMEM_COLS 128
+// 3xTF32 only: the tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
+// accumulation steps (K = 18432 for the ResNet-50 3x3 projection).  Rotating over 4 accumulators keeps each partial
+// sum 4x smaller (so its ulp, and the bias, shrink accordingly); the epilogue adds them in round-to-nearest fp32.
+#define PJ_SPLIT_ACCS 4
 
 struct PjGeom {
   int N, H, W, Cin, Cout, taps;   // taps = 1 (1x1) or 9 (3x3, pad 1)
@@ -132,6 +136,7 @@ pj_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                float* __restrict__ y, float* __restrict__ part_mean, float* __restrict__ part_m2,
                float* __restrict__ part_cnt, const PjGeom g) {
   constexpr int NOPS = SPLIT3 ? 2 : 1;
+  constexpr int NACC = SPLIT3 ? PJ_SPLIT_ACCS : 1;
   constexpr uint32_t STAGE_BYTES = NOPS * (PJ_A_BYTES + PJ_B_BYTES);
   extern __shared__ uint8_t pj_smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)pj_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -153,7 +158,7 @@ pj_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pj_smem(tmem_slot)), "r"(PJ_TMEM_COLS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pj_smem(tmem_slot)), "r"(PJ_TMEM_COLS * NACC));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -200,13 +205,15 @@ pj_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
       for (int k = 0; k < PJ_BLOCK_K / PJ_UMMA_K; ++k) {
         const uint64_t adv = (uint64_t)((k * PJ_UMMA_K * 4) >> 4);
-        const uint32_t first = (kb | k) != 0;
         if (SPLIT3) {
           const uint64_t a_lo = pj_desc(sa + PJ_A_BYTES + PJ_B_BYTES), b_lo = pj_desc(sa + 2 * PJ_A_BYTES + PJ_B_BYTES);
-          pj_mma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, first);
-          pj_mma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-          pj_mma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+          const uint32_t acc = tmem_base + (uint32_t)((kb % NACC) * PJ_TMEM_COLS);
+          const uint32_t first = (kb >= NACC || k != 0) ? 1u : 0u;      // the first k-block of each accumulator overwrites
+          pj_mma_tf32(acc, a_lo + adv, b_hi + adv, idesc, first);
+          pj_mma_tf32(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+          pj_mma_tf32(acc, a_hi + adv, b_hi + adv, idesc, 1u);
         } else {
+          const uint32_t first = (kb | k) != 0;
           pj_mma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, first);
         }
       }
@@ -229,6 +236,15 @@ pj_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     for (int c = 0; c < PJ_BLOCK_N; c += 32) {
       uint32_t v[32];
       pj_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (SPLIT3) {
+        const int used = num_kb < NACC ? num_kb : NACC;           // accumulators that received at least one k-block
+        for (int a = 1; a < used; ++a) {
+          uint32_t u[32];
+          pj_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * PJ_TMEM_COLS + c), u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float f = valid ? __uint_as_float(v[j]) : 0.f;
@@ -270,7 +286,7 @@ pj_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(PJ_TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(PJ_TMEM_COLS * NACC));
   }
 }
 

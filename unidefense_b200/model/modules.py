@@ -212,3 +212,7 @@ class SpatialDynamicFilter(_DynamicFilter):
         self.layer1 = nn.Sequential(nn.Conv2d(depth, depth, 3, 1, 1, bias=bias), norm(depth, affine=affine),
                                     activation())
         self.layer2 = nn.Sequential(nn.Conv2d(5, 1, 1, bias=bias), nn.Sigmoid())
+        # the 3x3 kernel is stored [Cout, ky, kx, Cin] in memory (channels_last): that IS the K-major B operand of the
+        # implicit GEMM, so no per-step weight re-layout.  Shape, state_dict key and values are unchanged.
+        conv = self.layer1[0]
+        conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)

@@ -312,7 +312,8 @@ class _ProjConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, precision, want_stats):
-        L.require_cuda_f32(weight)
+        if not weight.is_cuda or weight.dtype != torch.float32:
+            raise RuntimeError("proj_conv: weight must be a CUDA fp32 tensor (no CPU fallback)")
         if x.dtype != torch.float32 or not x.is_cuda:
             raise RuntimeError("proj_conv: x must be a CUDA fp32 tensor (no CPU fallback)")
         N, Cin, H, W = x.shape
@@ -330,9 +331,14 @@ class _ProjConv(torch.autograd.Function):
             x_hi = torch.empty(N, H, W, Cin, device=dev, dtype=torch.float32)
             x_lo = torch.empty_like(x_hi) if split else None
             L.check(lib.ud_proj_prep_x(L.ptr(xc), L.ptr(x_hi), L.ptr(x_lo), N, Cin, H * W, L.stream()), "proj_prep_x")
-        wc = weight.contiguous()
-        if k == 1 and not split:
-            w_hi, w_lo = wc, None
+        w_cl = k > 1 and weight.is_contiguous(memory_format=torch.channels_last)
+        wc = weight if w_cl else weight.contiguous()
+        if not split and (k == 1 or w_cl):
+            w_hi, w_lo = wc, None                      # [Cout, Cin] / channels_last [Cout, ky, kx, Cin]: already K-major
+        elif w_cl:                                     # split a K-major weight: taps = 1 re-layout is the identity
+            w_hi = torch.empty(Cout, k * k, Cin, device=dev, dtype=torch.float32)
+            w_lo = torch.empty_like(w_hi)
+            L.check(lib.ud_proj_prep_w(L.ptr(wc), L.ptr(w_hi), L.ptr(w_lo), Cout, k * k * Cin, 1, L.stream()), "proj_prep_w")
         else:
             w_hi = torch.empty(Cout, k * k, Cin, device=dev, dtype=torch.float32)
             w_lo = torch.empty_like(w_hi) if split else None
