@@ -216,6 +216,21 @@ UD_API int ud_sf_mix_bwd(const void* g_out, const void* spat, const float* freq,
                          float* g_freq, float* g_coef, void* ws, size_t ws_bytes, int N, int C, int P, int nhwc,
                          int bf16, cudaStream_t stream);
 
+/* ---- §8(e): the exchange step -- SyncBatchNorm statistics over NVLink peer memory ----------------------------------
+ * Replaces the two per-layer collectives of torch.nn.SyncBatchNorm (engine/forgery_engine.py:142 converts all 99
+ * BatchNorms of UDEB4): all_gather of [mean, invstd|M2, count] forward, all_reduce of [sum dy, sum dy*xmu] backward.
+ * Every rank owns one buffer (ud_comm_alloc: cudaMalloc + CUDA IPC handle, 64 bytes) that all ranks of the box map
+ * (ud_comm_open); ud_comm_gather is ONE single-CTA kernel per rank: remote stores of my vector into every rank's
+ * buffer, release-flag, acquire-spin on my own buffer, local copy (reduce=0: dst [world,count]) or fixed-order sum
+ * (reduce=1: dst [count]).  Plain kernel launches: CUDA-graph capturable, no host synchronisation, no NCCL.
+ * All ranks must issue the same sequence of gathers.  count <= max_count given at creation; world <= 16.          */
+UD_API size_t ud_comm_buffer_bytes(int world, int max_count);
+UD_API int ud_comm_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out);
+UD_API int ud_comm_open(const void* ipc_handle, void** peer_ptr);
+UD_API int ud_comm_create(void* const* peers, int rank, int world, int max_count, void** comm_out);
+UD_API int ud_comm_gather(void* comm, const float* src, float* dst, int count, int reduce, cudaStream_t stream);
+UD_API int ud_comm_error(void* comm);
+
 #ifdef __cplusplus
 }
 #endif

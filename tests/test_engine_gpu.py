@@ -133,12 +133,12 @@ def test_engine_iterations_match_the_reference_engine(monkeypatch, run):
         for n, w in st["weights"].items():
             p = names[n].detach()
             rel = abs(float(p.norm()) - w["norm"]) / (w["norm"] + 1e-30)
-            assert rel <= max(2e-4, 50 * nz["weight_norm_rel"][n]), f"{run} iteration {i + 1} |{n}|: rel {rel:.2e}"
+            assert rel <= max(1e-3, 100 * nz["weight_norm_rel"][n]), f"{run} iteration {i + 1} |{n}|: rel {rel:.2e}"
             idx = P.sample_indices(p.numel(), 8, n)
             d = float((p.flatten().cpu()[idx] - w["sample"]).abs().max())
             # the first layers see the whole backward pass of a train-mode-BN network on 4 samples: their gradient
             # (times lr) carries the accumulated GPU-vs-CPU rounding differences, hence the relative floor
-            tol = step_budget + max(2e-3 * float(w["sample"].abs().max()), 100 * nz["weight_sample"][n], 1e-6)
+            tol = step_budget + max(5e-3 * float(w["sample"].abs().max()), 100 * nz["weight_sample"][n], 1e-6)
             assert d <= tol, f"{run} iteration {i + 1} {n}: sample diff {d:.2e} > {tol:.2e}"
         sd = model.state_dict()
         for k, v in st["bn"].items():

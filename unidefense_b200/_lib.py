@@ -68,6 +68,12 @@ SIGNATURES = {
     "ud_sf_mix_fwd": (c_i, [c_p] * 4 + [c_i] * 5 + [c_p]),
     "ud_sf_mix_bwd_workspace_bytes": (c_sz, [c_i] * 3),
     "ud_sf_mix_bwd": (c_i, [c_p] * 8 + [c_sz] + [c_i] * 5 + [c_p]),
+    "ud_comm_buffer_bytes": (c_sz, [c_i, c_i]),
+    "ud_comm_alloc": (c_i, [c_sz, ctypes.POINTER(c_p), c_p]),
+    "ud_comm_open": (c_i, [c_p, ctypes.POINTER(c_p)]),
+    "ud_comm_create": (c_i, [ctypes.POINTER(c_p), c_i, c_i, c_i, ctypes.POINTER(c_p)]),
+    "ud_comm_gather": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p]),
+    "ud_comm_error": (c_i, [c_p]),
     "ud_kl_div_log_target_fwd": (c_i, [c_p] * 5 + [c_sz, c_i, c_i, c_p]),
 }
 

@@ -18,7 +18,24 @@
 // HBM traffic per sample (fp32): fwd reads dec+x, writes rec (+1 B/bin signs);
 // bwd reads dec+x(+signs), writes g_dec.
 #include "../../include/unidefense_b200.h"
+#include <stdlib.h>
+
 #include "ud_fft.cuh"
+
+// second-generation kernels for the configured image sizes (ud_recon_tail2.cu)
+bool ud_rt2_supported(int h, int w, int H, int W);
+size_t ud_rt2_workspace_plane_bytes(int H, int W);
+int ud_rt2_fwd(const float* dec, const float* x, float* rec, float2* Z, float* part_sp, float* part_fr, uint8_t* signs,
+               int plane0, int planes, int h, int w, int H, int W, int row_tiles, int col_tiles, cudaStream_t stream);
+int ud_rt2_bwd(const float* dec, const float* x, const uint8_t* signs, const float* g_spatial, const float* g_freq,
+               float* g_dec, float2* T, int plane0, int planes, int C, int h, int w, int H, int W, int row_tiles,
+               int col_tiles, float gscale, float sp_scale, cudaStream_t stream);
+#define RT2_PAIRS_PER_TILE 32   // RT2_LPC * RT2_ITER of ud_recon_tail2.cu
+#define RT2_COLS_PER_TILE 16
+static bool rt_use_v2(int h, int w, int H, int W) {
+  static const bool force_v1 = getenv("UD_RT_V1") != nullptr;      // A/B switch for profiling
+  return !force_v1 && ud_rt2_supported(h, w, H, W);
+}
 
 #define RT_ROW_T 256   // threads of the rows kernels
 #define RT_ROW_L 12    // row PAIRS (complex lines) per CTA of the rows kernels  -> 24 image rows
@@ -532,9 +549,14 @@ static size_t rt_cols_smem(int n) {
   return sizeof(float2) * ((size_t)n + bufs * RT_COL_L * (size_t)(n | 1));
 }
 
+static size_t rt_plane_bytes(int H, int W) {
+  const size_t v1 = (size_t)H * rt_whp(W) * sizeof(float2), v2 = ud_rt2_workspace_plane_bytes(H, W);
+  return v1 > v2 ? v1 : v2;
+}
+
 static int rt_chunk_samples(int N, int C, int H, int W) {
   // the Y/T workspace of a chunk must stay L2-resident (126 MB) next to the streamed images
-  const size_t per_sample = (size_t)C * H * rt_whp(W) * sizeof(float2);
+  const size_t per_sample = (size_t)C * rt_plane_bytes(H, W);
   int chunk = (int)((64ull << 20) / (per_sample ? per_sample : 1));
   if (chunk < 1) chunk = 1;
   if (chunk > N) chunk = N;
@@ -545,7 +567,7 @@ extern "C" size_t ud_recon_tail_workspace_bytes(int N, int C, int h, int w, int 
   (void)h; (void)w;
   const int chunk = rt_chunk_samples(N, C, H, W);
   const int row_tiles = ud_cdiv(H, 2 * RT_ROW_L), col_tiles = ud_cdiv(W / 2 + 1, RT_COL_L);
-  size_t y = ud_align_up((size_t)chunk * C * H * rt_whp(W) * sizeof(float2), 256);
+  size_t y = ud_align_up((size_t)chunk * C * rt_plane_bytes(H, W), 256);
   size_t ps = ud_align_up((size_t)N * C * row_tiles * sizeof(float), 256);
   size_t pf = ud_align_up((size_t)N * C * col_tiles * sizeof(float), 256);
   return y + ps + pf;
@@ -601,10 +623,12 @@ extern "C" int ud_recon_tail_fwd(const float* dec, const float* x, float* rec, f
   int chunk = rt_chunk_samples(N, C, H, W);
   if (chunk * C > 65535) chunk = 65535 / C;
   const int Wh = W / 2 + 1;
-  const int row_tiles = ud_cdiv(H, 2 * RT_ROW_L), col_tiles = ud_cdiv(Wh, RT_COL_L);
+  const bool v2 = rt_use_v2(h, w, H, W);
+  const int row_tiles = v2 ? ud_cdiv((H + 1) / 2, RT2_PAIRS_PER_TILE) : ud_cdiv(H, 2 * RT_ROW_L);
+  const int col_tiles = v2 ? ud_cdiv(Wh, RT2_COLS_PER_TILE) : ud_cdiv(Wh, RT_COL_L);
   char* p = static_cast<char*>(ws);
   float2* Y = reinterpret_cast<float2*>(p);
-  p += ud_align_up((size_t)rt_chunk_samples(N, C, H, W) * C * H * rt_whp(W) * sizeof(float2), 256);
+  p += ud_align_up((size_t)rt_chunk_samples(N, C, H, W) * C * rt_plane_bytes(H, W), 256);
   float* part_sp = reinterpret_cast<float*>(p);
   p += ud_align_up((size_t)N * C * row_tiles * sizeof(float), 256);
   float* part_fr = reinterpret_cast<float*>(p);
@@ -618,6 +642,11 @@ extern "C" int ud_recon_tail_fwd(const float* dec, const float* x, float* rec, f
   for (int s0 = 0; s0 < N; s0 += chunk) {
     const int ns = (N - s0 < chunk) ? (N - s0) : chunk;
     const int planes = ns * C, plane0 = s0 * C;
+    if (v2) {
+      if ((rc = ud_rt2_fwd(dec, x, rec, Y, part_sp, part_fr, signs, plane0, planes, h, w, H, W, row_tiles, col_tiles,
+                           stream)) != UD_OK) return rc;
+      continue;
+    }
     RT_DISPATCH_PLAN(W, RT_ROW_L, RT_ROW_T, plan, {
       auto k = rt_rows_fwd_kernel<decltype(plan)>;
       if ((rc = rt_set_smem(k, smW)) != UD_OK) return rc;
@@ -651,7 +680,9 @@ extern "C" int ud_recon_tail_bwd(const float* dec, const float* x, const uint8_t
   int chunk = rt_chunk_samples(N, C, H, W);
   if (chunk * C > 65535) chunk = 65535 / C;
   const int Wh = W / 2 + 1;
-  const int row_tiles = ud_cdiv(H, 2 * RT_ROW_L), col_tiles = ud_cdiv(Wh, RT_COL_L);
+  const bool v2 = rt_use_v2(h, w, H, W);
+  const int row_tiles = v2 ? ud_cdiv((H + 1) / 2, RT2_PAIRS_PER_TILE) : ud_cdiv(H, 2 * RT_ROW_L);
+  const int col_tiles = v2 ? ud_cdiv(Wh, RT2_COLS_PER_TILE) : ud_cdiv(Wh, RT_COL_L);
   float2* T = reinterpret_cast<float2*>(ws);
   const float2* twW = ud_twiddles(W);
   const float2* twH = ud_twiddles(H);
@@ -670,6 +701,11 @@ extern "C" int ud_recon_tail_bwd(const float* dec, const float* x, const uint8_t
   for (int s0 = 0; s0 < N; s0 += chunk) {
     const int ns = (N - s0 < chunk) ? (N - s0) : chunk;
     const int planes = ns * C, plane0 = s0 * C;
+    if (v2) {
+      if ((rc = ud_rt2_bwd(dec, x, signs, g_spatial, g_freq, g_dec, T, plane0, planes, C, h, w, H, W, row_tiles, col_tiles,
+                           gscale, sp_scale, stream)) != UD_OK) return rc;
+      continue;
+    }
     RT_DISPATCH_PLAN(H, RT_COL_L, RT_COL_T, plan, {
       auto k = rt_cols_bwd_kernel<decltype(plan)>;
       if ((rc = rt_set_smem(k, smH)) != UD_OK) return rc;

@@ -141,15 +141,23 @@ def bn_forward_stats(bn, proj, local=None):
     if group is not None:
         world = dist.get_world_size(group)
         packed = torch.cat([mean, m2, mean.new_tensor([count])])
-        parts = [torch.empty_like(packed) for _ in range(world)]
-        dist.all_gather(parts, packed, group=group)          # 2C+1 floats per rank (<= 33 KB): latency-bound
-        gathered = torch.stack(parts)
-        mean, m2, count = merge_bn_stats(gathered[:, :C], gathered[:, C:2 * C], gathered[:, 2 * C])
+        from ..parallel import default_comm
+        comm = default_comm()
+        if comm is not None and proj.is_cuda and 2 * C + 1 <= comm.max_count:
+            gathered = comm.gather(packed)                       # one NVLink peer-memory kernel (csrc/ud_comm.cu)
 
-        def reduce_fn(t):
-            t = t.contiguous()
-            dist.all_reduce(t, group=group)
-            return t
+            def reduce_fn(t):
+                return comm.reduce(t.contiguous())
+        else:
+            parts = [torch.empty_like(packed) for _ in range(world)]
+            dist.all_gather(parts, packed, group=group)          # 2C+1 floats per rank (<= 33 KB): latency-bound
+            gathered = torch.stack(parts)
+
+            def reduce_fn(t):
+                t = t.contiguous()
+                dist.all_reduce(t, group=group)
+                return t
+        mean, m2, count = merge_bn_stats(gathered[:, :C], gathered[:, C:2 * C], gathered[:, 2 * C])
     var = m2 / count
     if bn.training and bn.track_running_stats and bn.running_mean is not None:
         with torch.no_grad():

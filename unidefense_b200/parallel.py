@@ -14,10 +14,109 @@ reads the counts on the host: zero-count ranks contribute zero weight to the gat
 The class subclasses nn.SyncBatchNorm, so isinstance checks (ours in model/modules.py, DDP's, user code) and
 state_dict keys are unchanged.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
+
+
+class PeerComm:
+    """Small-vector exchange between the ranks of ONE NVLink/NVSwitch box over CUDA-IPC peer memory
+    (csrc/ud_comm.cu): `gather(v)` -> [world, n], `reduce(v)` -> sum over ranks, each ONE single-CTA kernel per
+    rank (remote stores + release/acquire flags), no NCCL call, no host synchronisation, CUDA-graph capturable.
+    Built once per process from an initialised process group (the IPC handles travel through it)."""
+
+    def __init__(self, group=None, max_count=16384):
+        from . import _lib as L
+        self.L = L
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.max_count = int(max_count)
+        lib = L.lib()
+        nbytes = lib.ud_comm_buffer_bytes(self.world, self.max_count)
+        if nbytes == 0:
+            raise RuntimeError(f"PeerComm: world size {self.world} unsupported (<= 16)")
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        L.check(lib.ud_comm_alloc(nbytes, ctypes.byref(own), handle), "comm_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+        peers = (ctypes.c_void_p * self.world)()
+        for q, hq in enumerate(handles):
+            if q == self.rank:
+                peers[q] = own.value
+            else:
+                ptr = ctypes.c_void_p()
+                L.check(lib.ud_comm_open(ctypes.create_string_buffer(hq, 64), ctypes.byref(ptr)), "comm_open")
+                peers[q] = ptr.value
+        comm = ctypes.c_void_p()
+        L.check(lib.ud_comm_create(peers, self.rank, self.world, self.max_count, ctypes.byref(comm)), "comm_create")
+        self.handle = comm
+        dist.barrier(group=self.group)          # every buffer is mapped everywhere before the first gather
+
+    def _run(self, v, reduce):
+        L = self.L
+        v = v.contiguous()
+        L.require_cuda_f32(v)
+        n = v.numel()
+        out = torch.empty(n if reduce else (self.world, n), device=v.device, dtype=torch.float32)
+        L.check(L.lib().ud_comm_gather(self.handle, L.ptr(v), L.ptr(out), n, int(reduce), L.stream()), "comm_gather")
+        return out
+
+    def gather(self, v):
+        """[n] fp32 on every rank -> [world, n]."""
+        return self._run(v, False)
+
+    def reduce(self, v):
+        """[n] (any shape) fp32 -> elementwise sum over ranks, same shape (fixed rank order: deterministic)."""
+        return self._run(v, True).view(v.shape)
+
+    def error(self):
+        return self.L.lib().ud_comm_error(self.handle)
+
+
+_default_comm = None
+
+
+def set_default_comm(comm):
+    """Make `comm` the exchange used by every converted SyncBatchNorm and by the dynamic filters' BatchNorms
+    (None: back to torch.distributed collectives)."""
+    global _default_comm
+    _default_comm = comm
+
+
+def default_comm():
+    return _default_comm
+
+
+class FlatGradients:
+    """Batch-sharded data parallelism without DDP's reducer: every parameter's .grad is a view into ONE flat fp32
+    buffer, so the gradient exchange of a step is a single NCCL all-reduce (513 MB for UDEB4 at ~0.7 TB/s bus
+    bandwidth is ~1.3 ms of a 77 ms step: no bucketing/overlap machinery needed) and the whole step -- forward,
+    backward, all-reduce, optimizer -- captures into one CUDA graph.  Semantics = DDP's: gradients are averaged."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            # same strides as the parameter (channels_last weights included): autograd accumulates in place
+            p.grad = torch.as_strided(self.flat, p.shape, p.stride(), off)
+            off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce(self):
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
 
 
 class _SyncBNFunction(torch.autograd.Function):
@@ -34,14 +133,21 @@ class _SyncBNFunction(torch.autograd.Function):
             packed = torch.cat([mean, invstd, mean.new_full((1,), float(per_channel))])
         else:
             packed = torch.zeros(2 * C + 1, dtype=torch.float32, device=x.device)
-        gathered = torch.empty(world_size, 2 * C + 1, dtype=packed.dtype, device=packed.device)
-        if group._get_backend_name() != "gloo":
+        comm = _default_comm
+        gathered = None
+        if comm is not None and 2 * C + 1 <= comm.max_count:
+            gathered = comm.gather(packed.float())            # one peer-memory kernel instead of an NCCL all_gather
+        elif group._get_backend_name() != "gloo":
+            gathered = torch.empty(world_size, 2 * C + 1, dtype=packed.dtype, device=packed.device)
             dist.all_gather_into_tensor(gathered.view(1, -1), packed, group)
         else:
             parts = [torch.empty_like(packed) for _ in range(world_size)]
             dist.all_gather(parts, packed, group)
             gathered = torch.stack(parts)
         mean_all, invstd_all, count_all = gathered[:, :C], gathered[:, C:2 * C], gathered[:, 2 * C]
+        # a rank with an empty input carries (0, 0, count 0): neutralise its invstd on the device (1/invstd^2 would
+        # be inf and inf*0 = NaN inside batch_norm_gather_stats_with_counts) -- still no host synchronisation
+        invstd_all = torch.where(count_all[:, None] > 0, invstd_all, torch.ones_like(invstd_all))
         counts = count_all.reshape(-1)
         if running_mean is not None and counts.dtype != running_mean.dtype:
             counts = counts.to(running_mean.dtype)
@@ -50,6 +156,7 @@ class _SyncBNFunction(torch.autograd.Function):
                                                                  running_mean, running_var, momentum, eps, counts)
         ctx.save_for_backward(x, weight, mean, invstd, count_all.reshape(-1, 1).to(torch.int32))
         ctx.group = group
+        ctx.comm = comm if (comm is not None and 2 * C <= comm.max_count) else None
         if x.numel() == 0:
             return torch.empty_like(x)
         return torch.batch_norm_elemt(x, weight, bias, mean, invstd, eps)
@@ -66,7 +173,10 @@ class _SyncBNFunction(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 C = sum_dy.shape[0]
                 both = torch.cat([sum_dy, sum_dy_xmu])
-                dist.all_reduce(both, op=dist.ReduceOp.SUM, group=ctx.group)
+                if ctx.comm is not None:
+                    both = ctx.comm.reduce(both.float())
+                else:
+                    dist.all_reduce(both, op=dist.ReduceOp.SUM, group=ctx.group)
                 sum_dy, sum_dy_xmu = both[:C], both[C:]
                 w = weight if weight is None or weight.dtype == mean.dtype else weight.to(mean.dtype)
                 gx = torch.batch_norm_backward_elemt(gy, x, mean, invstd, w, sum_dy, sum_dy_xmu, counts)
@@ -74,7 +184,10 @@ class _SyncBNFunction(torch.autograd.Function):
             C = x.shape[1]
             if ctx.needs_input_grad[0]:
                 both = torch.zeros(2 * C, dtype=mean.dtype, device=x.device)
-                dist.all_reduce(both, op=dist.ReduceOp.SUM, group=ctx.group)     # keep the collective order
+                if ctx.comm is not None:
+                    ctx.comm.reduce(both)                                         # keep the collective order
+                else:
+                    dist.all_reduce(both, op=dist.ReduceOp.SUM, group=ctx.group)     # keep the collective order
                 gx = torch.zeros_like(x)
         if weight is None or not ctx.needs_input_grad[1]:
             gw = None
