@@ -98,6 +98,45 @@ def alg_bytes(arch, N, R, n_real):
             "recon_tail_bwd": n_real * (dec + img) + N * dec}
 
 
+# kernel-name pattern -> op group of hot_path.ops_ms_per_step (device time per kernel from CUPTI records)
+KERNEL_GROUPS = [("recon_tail_fwd", r"rt2?_(rows_fwd|cols_fwd)_kernel|rt_finalize_kernel"),
+                 ("recon_tail_bwd", r"rt2?_(rows_bwd|cols_bwd)_kernel"),
+                 ("in_act_fwd", r"ia_fwd"), ("in_act_bwd", r"ia_bwd|ia_param_grad"),
+                 ("tanh_fwd", r"ia_tanh_fwd"), ("tanh_bwd", r"ia_tanh_bwd"),
+                 ("attn_prep", r"at_prep_kernel"), ("rfft2_cat", r"at_r2c_kernel"), ("irfft2_cat", r"at_c2r_kernel"),
+                 ("attn_fuse_fwd", r"at_fuse_fwd"), ("attn_fuse_bwd", r"at_fuse_bwd|at_sum_partials"),
+                 ("bn_stats", r"df_bn_stats|pj_merge"), ("dyfi_mask_fwd", r"df_mask_fwd"),
+                 ("dyfi_mask_bwd", r"df_mask_bwd|df_w2_reduce"), ("bn_bwd", r"df_bn_bwd"),
+                 ("proj_fwd", r"pj_gemm"), ("proj_prep", r"pj_prep"), ("triplet", r"ls_triplet"),
+                 ("factorization", r"ls_fac"), ("mask_kl", r"ls_mask_kl|ls_kl_log|ls_sum_kernel"),
+                 ("comm_gather", r"cm_gather"), ("sf_pack", r"sf_pack"), ("sf_mix", r"sf_mix|sf_sum"),
+                 ("perturb", r"pt_|fs_")]
+
+
+def cupti_kernel_times(run_step, steps):
+    """{group: (launches, total ms)} of OUR kernels over `steps` eager steps, device durations from CUPTI kernel
+    records (torch.profiler) -- unlike host-recorded events they do not include launch gaps of a host-bound stream."""
+    import re
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            run_step()
+        torch.cuda.synchronize()
+    out = {}
+    pats = [(g, re.compile(p)) for g, p in KERNEL_GROUPS]
+    for k in prof.key_averages():
+        name = k.key
+        t_us = getattr(k, "device_time_total", None)
+        if t_us is None:
+            t_us = getattr(k, "cuda_time_total", 0.0)
+        for g, pat in pats:
+            if pat.search(name):
+                c, t = out.get(g, (0, 0.0))
+                out[g] = (c + k.count, t + t_us / 1e3)
+                break
+    return out
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -477,11 +516,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    ddp_graph = world > 1 and (args.graph == "on" or os.environ.get("UD_BENCH_DDP_GRAPH", "0") == "1")
+    flat_dp = world > 1 and args.dp == "flat"
+    ddp_graph = world > 1 and (flat_dp or args.graph == "on" or os.environ.get("UD_BENCH_DDP_GRAPH", "0") == "1")
+    if args.graph == "off":
+        ddp_graph = False
     if world > 1:
-        if ddp_graph:   # whole-network capture with DDP: no NCCL watchdog event queries while a stream captures
-            os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
-            os.environ["NCCL_ASYNC_ERROR_HANDLING"] = "0"
         dist.init_process_group("nccl", device_id=dev)
     from unidefense_b200 import _lib as L
     from unidefense_b200 import ops
@@ -505,12 +544,24 @@ def run_ours(args):
         else:       # same math and collectives, without torch's per-layer device->host sync (unidefense_b200/parallel.py)
             from unidefense_b200.parallel import convert_sync_batchnorm
             model = convert_sync_batchnorm(model)
-        ctor_stream = torch.cuda.Stream() if ddp_graph else torch.cuda.current_stream()
-        with torch.cuda.stream(ctor_stream):       # DDP must be built on a side stream to be capturable later
-            ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
-        torch.cuda.current_stream().wait_stream(ctor_stream)
+        if flat_dp:
+            # B200-native data parallelism (unidefense_b200/parallel.py): SyncBatchNorm statistics over NVLink peer
+            # memory (one single-CTA kernel per exchange, csrc/ud_comm.cu) and ONE NCCL all-reduce of a flat gradient
+            # buffer -- no DDP reducer, so the whole step (collectives included) replays as one CUDA graph
+            from unidefense_b200.parallel import FlatGradients, PeerComm, set_default_comm
+            comm = PeerComm(max_count=16384)
+            set_default_comm(comm)
+            ddp = model
+            flat = FlatGradients(model.parameters())
+        else:
+            ctor_stream = torch.cuda.Stream() if ddp_graph else torch.cuda.current_stream()
+            with torch.cuda.stream(ctor_stream):       # DDP must be built on a side stream to be capturable later
+                ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
+            torch.cuda.current_stream().wait_stream(ctor_stream)
+            flat = None
     else:
         ddp = model
+        flat = None
     params = [p for p in model.parameters() if p.requires_grad]
     # whole-step CUDA graph: validated single-GPU; under DDP the NCCL capture dead-locked on this stack (round 1),
     # so multi-GPU runs stay eager unless --graph on is forced
@@ -532,15 +583,24 @@ def run_ours(args):
                 + LAMBDAS["mask"] * ld["spat_mask"].mean() + LAMBDAS["triplet"] * tri
                 + LAMBDAS["recons"] * ld["spatial"][:nr].mean() + LAMBDAS["freq"] * ld["freq"][:nr].mean())
         loss.backward()
+        if flat is not None:
+            flat.all_reduce()                       # one NCCL all-reduce (avg) of every gradient
         opt.step()
         return loss
 
+    def zero_grads():
+        if flat is not None:
+            flat.zero()                             # gradients are views into the flat buffer: keep them
+        else:
+            opt.zero_grad(set_to_none=True)
+
     def eager_step(x, labels):
-        opt.zero_grad(set_to_none=True)
+        zero_grads()
         return body(x, labels)
 
     step = eager_step
     graph_note = "off" if world == 1 or args.graph == "off" else "off (eager under DDP: NCCL capture not validated)"
+    graph_launches = 0
     if use_graph:
         # Whole-step CUDA graph (forward, loss, backward incl. DDP/SyncBN NCCL collectives, fused AdamW): the step
         # issues ~3000 small kernels and is host-launch-bound, worst with 8 ranks sharing the box's cores.
@@ -548,16 +608,19 @@ def run_ours(args):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(11 if world > 1 else 3):      # DDP needs 11 side-stream iterations before capture
+                for _ in range(11 if (world > 1 and flat is None) else 3):   # DDP needs 11 side-stream iterations before capture
                     eager_step(x_dev, l_dev)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            opt.zero_grad(set_to_none=True)
+            if flat is None:
+                opt.zero_grad(set_to_none=True)
             l0 = L.lib().ud_launch_count()
             err = None
             try:
                 with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    if flat is not None:
+                        flat.zero()
                     static_loss = body(x_dev, l_dev)
             except Exception as e:                   # noqa: BLE001
                 err = e
@@ -605,7 +668,6 @@ def run_ours(args):
     if sampler is not None:
         sampler.start()
     graphed = graph_note == "whole step captured"
-    L.PROFILE = None if graphed else {}
     launches0 = L.lib().ud_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -617,16 +679,26 @@ def run_ours(args):
     launches = graph_launches * args.steps if graphed else L.lib().ud_launch_count() - launches0
     ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.summary() if sampler is not None else None
-    if graphed:
-        # events cannot be recorded inside a replayed graph: the per-op device times behind `roofline` come from
-        # the same step issued eagerly right after the timed region (same inputs, same kernels, L2 flushed)
-        L.PROFILE = {}
-        for _ in range(args.steps):
-            flush.zero_()
-            eager_step(x_dev, l_dev)
-        torch.cuda.synchronize()
-    prof = L.profile_summary()
+    # per-op device times behind `roofline` / `hot_path`: the same step issued eagerly right after the timed region
+    # (same inputs, same kernels, L2 flushed), kernel durations taken from CUPTI records; host-recorded events (the
+    # round-1 method) are only the fallback because in a host-bound eager stream they include the launch gaps
     L.PROFILE = None
+    prof_steps = min(args.steps, 3)
+
+    def _prof_step():
+        flush.zero_()
+        eager_step(x_dev, l_dev)
+    try:
+        prof = cupti_kernel_times(_prof_step, prof_steps)
+        prof_how = "CUPTI kernel records (torch.profiler) of the step re-issued eagerly after the timed region"
+    except Exception as e:                   # noqa: BLE001
+        L.PROFILE = {}
+        for _ in range(prof_steps):
+            _prof_step()
+        torch.cuda.synchronize()
+        prof = L.profile_summary()
+        L.PROFILE = None
+        prof_how = f"CUDA events around each C-ABI call (CUPTI unavailable: {type(e).__name__})"
 
     # end to end through the public API with HOST buffers: pinned H2D of the batch + D2H of the loss every step
     barrier()
@@ -658,7 +730,7 @@ def run_ours(args):
     if rank == 0:
         pk, pk_kind = peaks()
         ab = alg_bytes(arch, nb, res, nr)
-        ops_ms = {k: v[1] / args.steps for k, v in prof.items()}
+        ops_ms = {k: v[1] / prof_steps for k, v in prof.items()}
         timed = {k: (ab[k] / (ops_ms[k] * 1e-3) / 1e9) for k in ab if k in ops_ms and ops_ms[k] > 0}
         dom = max((k for k in ops_ms if k in ab), key=lambda k: ops_ms[k], default=None)
         roof = None
@@ -666,10 +738,13 @@ def run_ours(args):
             ach = timed[dom]
             roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "peak_kind": pk_kind,
                     "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4), "traffic": TRAFFIC.get(dom),
-                    "alg_bytes_per_launch": ab[dom] // max(prof[dom][0] // args.steps, 1),
+                    "alg_bytes_per_launch": ab[dom] // max(prof[dom][0] // prof_steps, 1),
+                    "launches_per_step": prof[dom][0] // prof_steps, "timed_with": prof_how,
                     "ms_per_step_in_kernel": round(ops_ms[dom], 4)}
         sf_ms = sum(v for k, v in ops_ms.items() if k.startswith("sf_"))     # SFConv glue (backbone, §8f) -- not recon path
-        hot_ms = sum(ops_ms.values()) - sf_ms
+        dense_ms = ops_ms.get("proj_fwd", 0.0) + ops_ms.get("proj_prep", 0.0)   # tcgen05 projections: tensor-pipe bound
+        comm_ms = ops_ms.get("comm_gather", 0.0)
+        hot_ms = sum(ops_ms.values()) - sf_ms - dense_ms - comm_ms
         mbs = RECON_MB_PER_SAMPLE.get((arch, res))
         line = {"metric": METRIC, "value": round(nb * world / (ms * 1e-3), 2), "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
@@ -678,7 +753,9 @@ def run_ours(args):
                                        f"{res}x{res}, per-GPU batch {nb}, random init",
                            "hot_path_dtype": "f32", "backbone": f"stock torch, {args.dtype} autocast"
                                        + (f", channels_last ({args.channels_last})" if args.channels_last != "none" else ""),
-                           "parallelism": f"dp{world}" + (f" (DDP + SyncBatchNorm[{args.syncbn}], NCCL)" if world > 1 else ""),
+                           "parallelism": f"dp{world}" + ((" (flat-gradient NCCL all-reduce + SyncBatchNorm over NVLink peer memory)"
+                                                            if flat is not None else
+                                                            f" (DDP + SyncBatchNorm[{args.syncbn}], NCCL)") if world > 1 else ""),
                            "cuda_graph": graph_note,
                            "l2": "256 MB buffer written between timed iterations; per-step activations >> 126 MB L2"},
                 "clocks": clocks,
@@ -689,6 +766,8 @@ def run_ours(args):
                 "roofline": roof,
                 "hot_path": {"kernel_ms_per_step": round(hot_ms, 3), "share_of_step": round(hot_ms / ms, 4),
                              "sfconv_glue_kernel_ms_per_step": round(sf_ms, 3),
+                             "tcgen05_projection_ms_per_step": round(dense_ms, 3),
+                             "peer_exchange_ms_per_step": round(comm_ms, 3),
                              "alg_mb_per_sample": mbs,
                              "hbm_frac_of_recon_path_kernels": (round(mbs * 1e6 * nb / (hot_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4)
                                                                 if mbs else None),
@@ -738,6 +817,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="faces per CPU step of the reference / cpu_baseline leg")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the whole training step in a CUDA graph (auto: fall back to eager if capture fails)")
+    ap.add_argument("--dp", default="flat", choices=["flat", "ddp"],
+                    help="multi-GPU plumbing: flat = one flat-gradient all-reduce + peer-memory SyncBN statistics "
+                         "(CUDA-graph replay); ddp = torch DistributedDataParallel as the reference engines wrap it")
     ap.add_argument("--syncbn", default="ours", choices=["ours", "torch"],
                     help="multi-GPU BatchNorm conversion: torch.nn.SyncBatchNorm or the host-sync-free equivalent")
     ap.add_argument("--no-cpu-baseline", action="store_true")

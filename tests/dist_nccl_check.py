@@ -189,7 +189,9 @@ def main():
                 xi = xin.clone().requires_grad_()
                 y = net(xi)
                 (y * gout).sum().backward()
-                outs.append((y.detach(), xi.grad, [p.grad.clone() for p in net.parameters()], [bf.clone() for bf in net.buffers()]))
+                outs.append((y.detach(), torch.zeros_like(xi) if xi.grad is None else xi.grad,
+                             [torch.zeros_like(p) if p.grad is None else p.grad.clone()
+                                                   for p in net.parameters()], [bf.clone() for bf in net.buffers()]))
                 net.zero_grad()
             torch.testing.assert_close(outs[1][0], outs[0][0], rtol=1e-5, atol=1e-6)
             torch.testing.assert_close(outs[1][1], outs[0][1], rtol=1e-5, atol=1e-6)

@@ -133,3 +133,29 @@ def test_linearity_property_full_size():
     torch.testing.assert_close(fr2, 2 * fr, rtol=1e-5, atol=0)
     # Parseval: sum |D|^2 == sum d^2 (ortho) bounds the L1 spectrum: freq*C*H*Wh <= sqrt(2*bins*energy)
     assert torch.isfinite(fr).all() and (fr > 0).all()
+
+
+def test_rec_output_is_differentiable():
+    """out['rec'] = interpolate(dec) carries a gradient in the reference (model/unidefense.py:244): a loss on it must
+    reach dec (transposed bilinear resize), alone and together with the spatial/freq terms."""
+    from unidefense_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    dec = torch.tanh(torch.randn(2, 3, 19, 23, generator=g))
+    x = torch.rand(2, 3, 38, 40, generator=g) * 2 - 1
+    gr = torch.randn(2, 3, 38, 40, generator=g)
+    for with_losses in (False, True):
+        d = dec.cuda().requires_grad_()
+        rec, sp, fr = ops.recon_tail(d, x.cuda())
+        loss = (rec * gr.cuda()).sum() + ((0.3 * sp.sum() + fr.sum()) if with_losses else 0.0)
+        loss.backward()
+        d64 = dec.double().requires_grad_()
+        rec64, sp64, fr64 = O.recon_tail(d64, x.double())
+        loss64 = (rec64 * gr.double()).sum() + ((0.3 * sp64.sum() + fr64.sum()) if with_losses else 0.0)
+        loss64.backward()
+        torch.testing.assert_close(d.grad.cpu().double(), d64.grad, rtol=1e-4, atol=1e-5 * float(d64.grad.abs().max()))
+
+
+def test_unsupported_norm_is_rejected():
+    from unidefense_b200 import ops
+    with pytest.raises(ValueError, match="freq_norm"):
+        ops.recon_tail(torch.zeros(1, 3, 4, 4, device="cuda"), torch.zeros(1, 3, 8, 8, device="cuda"), norm="forward")

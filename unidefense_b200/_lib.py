@@ -157,6 +157,10 @@ def require_cuda_f32(*tensors):
             continue
         if not t.is_cuda:
             raise RuntimeError("unidefense_b200 kernels need CUDA tensors (no CPU fallback)")
+        if t.device.index != torch.cuda.current_device():
+            raise RuntimeError(f"tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}: "
+                               "the stream, workspace and twiddle tables belong to the current device "
+                               "(call torch.cuda.set_device(local_rank) as the reference engines do)")
         if t.dtype != torch.float32:
             raise RuntimeError(f"unidefense_b200 kernels are fp32; got {t.dtype}")
         if not t.is_contiguous():

@@ -21,7 +21,7 @@
 #include "ud_common.cuh"
 
 #define CM_MAX_WORLD 16
-#define CM_SPIN_LIMIT (1u << 27)      // ~ a second of polling, then give up loudly instead of hanging the GPU
+#define CM_SPIN_LIMIT (1u << 22)      // a few seconds of system-scope polling, then give up loudly instead of hanging the GPU
 
 struct UdCommDev {
   float* peer[CM_MAX_WORLD];          // base of every rank's buffer as mapped in THIS process (peer[rank] = my own)

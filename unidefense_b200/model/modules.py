@@ -140,7 +140,7 @@ def bn_forward_stats(bn, proj, local=None):
     reduce_fn = None
     if group is not None:
         world = dist.get_world_size(group)
-        packed = torch.cat([mean, m2, mean.new_tensor([count])])
+        packed = torch.cat([mean, m2, torch.full((1,), count, device=mean.device, dtype=mean.dtype)])   # fill kernel: no H2D copy
         from ..parallel import default_comm
         comm = default_comm()
         if comm is not None and proj.is_cuda and 2 * C + 1 <= comm.max_count:

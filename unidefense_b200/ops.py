@@ -4,6 +4,17 @@ import torch
 from . import _lib as L
 
 
+def norm_flag(norm):
+    """torch.fft `norm` argument -> the kernels' flag.  The reference forwards freq_norm verbatim to torch.fft
+    (model/unidefense.py:130-145,:246-249); 'forward' scaling is not on any shipped config and is rejected loudly
+    rather than silently computed as 'backward'."""
+    if norm in (None, "backward"):
+        return 0
+    if norm == "ortho":
+        return 1
+    raise ValueError(f"freq_norm={norm!r} is not supported by the sm_100a kernels (None / 'backward' / 'ortho')")
+
+
 class _ReconTail(torch.autograd.Function):
     """a1: model/unidefense.py:244-253 / :423-433 / :618-628."""
 
@@ -31,7 +42,7 @@ class _ReconTail(torch.autograd.Function):
         if need_grad:
             ctx.save_for_backward(dec, x, signs)
         ctx.norm_ortho = int(norm_ortho)
-        ctx.mark_non_differentiable(rec)
+        ctx.set_materialize_grads(False)          # unused outputs (rec, in training) arrive as None, not as zeros
         return rec, spatial, freq
 
     @staticmethod
@@ -40,21 +51,29 @@ class _ReconTail(torch.autograd.Function):
         N, C, h, w = dec.shape
         H, W = x.shape[-2:]
         lib = L.lib()
-        gs = (g_spatial if g_spatial is not None else torch.zeros(N, device=x.device)).contiguous().float()
-        gf = (g_freq if g_freq is not None else torch.zeros(N, device=x.device)).contiguous().float()
-        g_dec = torch.empty_like(dec)
-        nws = lib.ud_recon_tail_workspace_bytes(N, C, h, w, H, W)
-        ws = L.workspace(nws, x.device)
-        L.check(lib.ud_recon_tail_bwd(L.ptr(dec), L.ptr(x), L.ptr(signs), L.ptr(gs), L.ptr(gf), L.ptr(g_dec),
-                                      L.ptr(ws), ws.numel(), N, C, h, w, H, W, ctx.norm_ortho, L.stream()),
-                "recon_tail_bwd")
+        g_dec = None
+        if g_spatial is not None or g_freq is not None:
+            gs = (g_spatial if g_spatial is not None else torch.zeros(N, device=x.device)).contiguous().float()
+            gf = (g_freq if g_freq is not None else torch.zeros(N, device=x.device)).contiguous().float()
+            g_dec = torch.empty_like(dec)
+            nws = lib.ud_recon_tail_workspace_bytes(N, C, h, w, H, W)
+            ws = L.workspace(nws, x.device)
+            L.check(lib.ud_recon_tail_bwd(L.ptr(dec), L.ptr(x), L.ptr(signs), L.ptr(gs), L.ptr(gf), L.ptr(g_dec),
+                                          L.ptr(ws), ws.numel(), N, C, h, w, H, W, ctx.norm_ortho, L.stream()),
+                    "recon_tail_bwd")
+        if g_rec is not None:
+            # rec = interpolate(dec) is differentiable in the reference (model/unidefense.py:244); the shipped engines
+            # never use that gradient, but a loss on out['rec'] gets the transposed resize, not silent zeros
+            g_up = torch.empty_like(dec)
+            L.check(lib.ud_bilinear_ac_bwd(L.ptr(g_rec.contiguous().float()), L.ptr(g_up), N * C, h, w, H, W, L.stream()),
+                    "bilinear_bwd")
+            g_dec = g_up if g_dec is None else g_dec + g_up
         return g_dec, None, None
 
 
 def recon_tail(dec, x, norm="ortho"):
-    """-> (rec [N,C,H,W], spatial [N], freq [N]); `rec` carries no grad (it is only returned for
-    visualisation/eval by the reference, engine/forgery_engine.py:343-347)."""
-    return _ReconTail.apply(dec, x, norm == "ortho")
+    """-> (rec [N,C,H,W], spatial [N], freq [N]), all differentiable w.r.t. dec (x is data)."""
+    return _ReconTail.apply(dec, x, norm_flag(norm))
 
 
 ACT_CODES = {"none": 0, "relu": 1, "swish": 2}
@@ -174,7 +193,7 @@ def attn_prep(pred, x, size, norm="ortho"):
     sd = torch.empty(N, C, h, w, device=x.device, dtype=torch.float32)
     fd = torch.empty(N, 2 * C, h, w // 2 + 1, device=x.device, dtype=torch.float32)
     L.check(L.lib().ud_attn_prep(L.ptr(pred), L.ptr(x), L.ptr(sd), L.ptr(fd), N, C, pred.shape[-2], pred.shape[-1],
-                                 x.shape[-2], x.shape[-1], h, w, int(norm == "ortho"), L.stream()), "attn_prep")
+                                 x.shape[-2], x.shape[-1], h, w, norm_flag(norm), L.stream()), "attn_prep")
     return sd, fd
 
 
@@ -211,7 +230,7 @@ class _Rfft2Cat(torch.autograd.Function):
 
 
 def rfft2_cat(x, norm="ortho"):
-    return _Rfft2Cat.apply(x, int(norm == "ortho"))
+    return _Rfft2Cat.apply(x, norm_flag(norm))
 
 
 class _Irfft2Cat(torch.autograd.Function):
@@ -232,7 +251,7 @@ class _Irfft2Cat(torch.autograd.Function):
 
 
 def irfft2_cat(xf, size, norm="ortho"):
-    return _Irfft2Cat.apply(xf, int(size[0]), int(size[1]), int(norm == "ortho"))
+    return _Irfft2Cat.apply(xf, int(size[0]), int(size[1]), norm_flag(norm))
 
 
 class _AttnFuse(torch.autograd.Function):
@@ -491,6 +510,9 @@ class _Factorization(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, b, off_w, eps):
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError("factorization_loss: only emb_a is differentiated (the engine passes emb_b detached, "
+                               "engine/abstract_engine.py:230); detach emb_b or swap the arguments")
         a, b = a.contiguous(), b.detach().contiguous()
         L.require_cuda_f32(a, b)
         N, F_ = a.shape
@@ -521,6 +543,9 @@ class _MaskKL(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pred, gt, fused=True):
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError("mask KL: the target is not differentiated (the engine detaches it, "
+                               "engine/abstract_engine.py:215-228); detach it")
         shape = pred.shape
         N = shape[0]
         p = pred.reshape(N, -1).contiguous()
