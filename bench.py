@@ -588,6 +588,47 @@ def run_ours(args):
         opt.step()
         return loss
 
+    def second_pass(x, labels, gt):
+        """engine/abstract_engine.py:286-376: perturbed forward (host-RNG augmentation dispatch incl. coral / style
+        transfer / noise / blur / downscale), KL mask alignment against pass 1 (steady state: cur_step > 10 %),
+        factorization loss against pass 1, 0.1-weighted CE / rec / freq, backward, optimizer step."""
+        perm_r = torch.arange(nr)[torch.randperm(nr)]
+        perm_f = torch.arange(nb - nr)[torch.randperm(nb - nr)]
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            out = ddp(x, pert_real_list=perm_r, pert_fake_list=perm_f, preserve_color=True)
+        ld = out["loss_dict"]
+        tri = sum(ops.triplet_loss(f, labels) for f in ld["triplet"])
+        fm = ops.mask_kl_loss(ld["freq_mask"], gt["freq_mask"])
+        sm = ops.mask_kl_loss(ld["spat_mask"], gt["spat_mask"])
+        fac = ops.factorization_loss(ld["factorization"].float(), gt["fac"])
+        loss = (0.1 * F.cross_entropy(out["cls_out"].float(), labels) + LAMBDAS["mask"] * fm + LAMBDAS["mask"] * sm
+                + LAMBDAS["triplet"] * tri + LAMBDAS["recons"] * 0.1 * ld["spatial"][:nr].mean()
+                + LAMBDAS["freq"] * 0.1 * ld["freq"][:nr].mean() + LAMBDAS["fac"] * fac)
+        loss.backward()
+        if flat is not None:
+            flat.all_reduce()
+        opt.step()
+        return loss
+
+    def two_pass_step(x, labels):
+        """One engine iteration = clean pass + perturbed pass (engine/abstract_engine.py:207-381), eager."""
+        zero_grads()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            out = ddp(x)
+        ld = out["loss_dict"]
+        gt = {"freq_mask": ld["freq_mask"].detach().clone(), "spat_mask": ld["spat_mask"].detach().clone(),
+              "fac": ld["factorization"].detach().float().clone()}
+        tri = sum(ops.triplet_loss(f, labels) for f in ld["triplet"])
+        loss = (F.cross_entropy(out["cls_out"].float(), labels) + LAMBDAS["mask"] * ld["freq_mask"].mean()
+                + LAMBDAS["mask"] * ld["spat_mask"].mean() + LAMBDAS["triplet"] * tri
+                + LAMBDAS["recons"] * ld["spatial"][:nr].mean() + LAMBDAS["freq"] * ld["freq"][:nr].mean())
+        loss.backward()
+        if flat is not None:
+            flat.all_reduce()
+        opt.step()
+        zero_grads()
+        return second_pass(x, labels, gt)
+
     def zero_grads():
         if flat is not None:
             flat.zero()                             # gradients are views into the flat buffer: keep them
@@ -598,9 +639,13 @@ def run_ours(args):
         zero_grads()
         return body(x, labels)
 
-    step = eager_step
+    step = two_pass_step if args.two_pass else eager_step
+    if args.two_pass:
+        use_graph = False                      # the augmentation dispatch draws from the host RNG every iteration
     graph_note = "off" if world == 1 or args.graph == "off" else "off (eager under DDP: NCCL capture not validated)"
     graph_launches = 0
+    if args.two_pass:
+        graph_note = "off (two-pass engine iteration: host-RNG augmentation dispatch)"
     if use_graph:
         # Whole-step CUDA graph (forward, loss, backward incl. DDP/SyncBN NCCL collectives, fused AdamW): the step
         # issues ~3000 small kernels and is host-launch-bound, worst with 8 ranks sharing the box's cores.
@@ -749,8 +794,11 @@ def run_ours(args):
         line = {"metric": METRIC, "value": round(nb * world / (ms * 1e-3), 2), "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": f"UniDefense {name} train step (fwd + engine pass-1 loss + bwd + AdamW amsgrad), "
-                                       f"{res}x{res}, per-GPU batch {nb}, random init",
+                "config": {"workload": (f"UniDefense {name} two-pass engine iteration (clean pass + perturbed pass with "
+                                        f"KL mask alignment and factorization loss, 2 x (fwd + bwd + AdamW amsgrad)), "
+                                        if args.two_pass else
+                                        f"UniDefense {name} train step (fwd + engine pass-1 loss + bwd + AdamW amsgrad), ")
+                                       + f"{res}x{res}, per-GPU batch {nb}, random init",
                            "hot_path_dtype": "f32", "backbone": f"stock torch, {args.dtype} autocast"
                                        + (f", channels_last ({args.channels_last})" if args.channels_last != "none" else ""),
                            "parallelism": f"dp{world}" + ((" (flat-gradient NCCL all-reduce + SyncBatchNorm over NVLink peer memory)"
@@ -825,6 +873,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recon-probe", action="store_true")
     ap.add_argument("--recon-only", action="store_true", help="run only the isolated recon-path probe (profiling aid)")
+    ap.add_argument("--two-pass", action="store_true",
+                    help="time the reference's full engine iteration (clean + perturbed pass, config C4) instead of one pass")
     ap.add_argument("--microbench", action="store_true",
                     help="C5 (BASELINE.json configs[4]): frequency-branch sweep R in {224,299,380} x B in {16..256}")
     args = ap.parse_args()

@@ -194,6 +194,17 @@ UD_API size_t ud_freq_style_workspace_bytes(int N, int C, int H, int W);
 UD_API int ud_freq_style_transfer(const float* content, const float* style, const float* lmda, float* out, void* ws,
                                   size_t ws_bytes, int N, int C, int H, int W, cudaStream_t stream);
 
+/* ---- a15: coral colour-statistics transfer (utils/operation.py:15-45; model/unidefense.py:189-191; no grad) ---------
+ * source[n] takes the per-channel mean / unbiased std and the 3x3 "f f^T + I" colour structure of target[n]:
+ *   out = sqrt~(cov_t) inv(sqrt~(cov_s)) (s - mean_s)/std_s * std_t + mean_t,  sqrt~(M) = U sqrt(D) Vh^T (the
+ *   reference's quirk: Vh transposed again).  The quirk depends on the sign of each singular vector, which the SVD
+ *   leaves open (LAPACK and cuSOLVER disagree): this kernel signs every eigenvector so that its largest-magnitude
+ *   component is positive; parity with the reference holds modulo that gauge (tests/test_perturb_gpu.py).
+ * source, target, out [N,3,HW] fp32; three launches for the whole batch, no host synchronisation.               */
+UD_API size_t ud_coral_workspace_bytes(int N, int HW);
+UD_API int ud_coral(const float* source, const float* target, float* out, void* ws, size_t ws_bytes, int N, int HW,
+                    cudaStream_t stream);
+
 /* ---- a16: stencil / resampling perturbations (no grad) ---------------------------------------------
  * random_blur (model/modules.py:15-16): torchvision gaussian_blur 5x5, sigma 1.1, reflect padding.   */
 UD_API int ud_gaussian_blur5(const float* x, float* y, int planes, int H, int W, cudaStream_t stream);

@@ -449,7 +449,9 @@ def make_engine(ref):
                          "weight_norm_rel": {k: abs(v["norm"] - b["weights"][k]["norm"]) / (v["norm"] + 1e-30)
                                              for k, v in a["weights"].items()},
                          "weight_sample": {k: float((v["sample"] - b["weights"][k]["sample"]).abs().max())
-                                           for k, v in a["weights"].items()}}
+                                           for k, v in a["weights"].items()},
+                         "dnorm_rel": {k: abs(v["dnorm"] - b["weights"][k]["dnorm"]) / (v["dnorm"] + 1e-30)
+                                       for k, v in a["weights"].items()}}
                         for a, b in zip(fix["steps"], alt["steps"])]
         fix["opt"] = opt
         out["runs"][name] = fix
@@ -487,6 +489,7 @@ def _engine_run(ref, Engine, eps, opt, n_steps):
     labels = torch.tensor([0] * (N // 2) + [1] * (N // 2))
     seeds = [engine_seed_for("blur", N // 2, N // 2), engine_seed_for("downscale", N // 2, N // 2)][:n_steps]
     steps = []
+    w0 = {n_: p_.detach().clone() for n_, p_ in model.named_parameters()}
     orig_dropout = F.dropout
     F.dropout = lambda t, p=0.5, training=True, inplace=False: t * 1.0
     try:
@@ -497,7 +500,9 @@ def _engine_run(ref, Engine, eps, opt, n_steps):
             wn = {}
             for n_, p_ in model.named_parameters():
                 idx = P.sample_indices(p_.numel(), 8, n_)
-                wn[n_] = {"norm": p_.detach().norm().item(), "sample": p_.detach().flatten()[idx].clone()}
+                d_ = p_.detach() - w0[n_]                      # what the optimizer did to this parameter so far
+                wn[n_] = {"norm": p_.detach().norm().item(), "sample": p_.detach().flatten()[idx].clone(),
+                          "dnorm": d_.norm().item(), "dsample": d_.flatten()[idx].clone()}
             bn = {k: v.clone() for k, v in model.state_dict().items()
                   if k.startswith(("bottleneck.running", "freq_filter.layer1.1.running", "spat_filter.layer1.1.running"))}
             steps.append({"seed": seed, "losses": losses, "cls_out": ret["cls_out"].detach().clone(), "weights": wn,

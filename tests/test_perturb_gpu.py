@@ -83,30 +83,60 @@ def test_spatial_style(golden_ops):
     torch.testing.assert_close(y0.flatten(2).sort(-1).values, style.cuda().flatten(2).sort(-1).values, rtol=0, atol=1e-6)
 
 
-def test_coral_batch(golden_ops):
-    """coral keeps the reference's U*sqrt(D)*Vh^T 'square root', whose value depends on the SVD library's sign
-    convention (fp32 and fp64 LAPACK already differ by O(1)).  Checked here: (1) everything around
-    the factorisation against the oracle formula fed with the SAME device factorisation; (2) the CPU-LAPACK
-    fixtures when the device convention happens to agree."""
-    from unidefense_b200 import ops
-    g = torch.Generator().manual_seed(4)
-    src = (torch.rand(3, 3, 40, 40, generator=g) * 2 - 1).cuda()
-    tgt = (torch.rand(3, 3, 40, 40, generator=g) * 1.2 - 0.5).cuda()
-    y = ops.coral_batch(src, tgt)
-    _, _, _, s_cov = ops._coral_stats(src)
-    _, _, _, t_cov = ops._coral_stats(tgt)
-    for n in range(3):
-        s_n, _, _, _ = O.coral_stats(src[n].double().cpu())
-        _, t_mean, t_std, _ = O.coral_stats(tgt[n].double().cpu())
+def _coral_candidates(source, target):
+    """The reference's coral (utils/operation.py:20-45) in fp64 for every sign pattern of the two SVDs: its
+    U*sqrt(D)*Vh^T 'square root'  equals U*sqrt(D)*U for the symmetric positive definite f f^T + I and
+    changes with the sign of each singular vector -- a gauge the SVD leaves open.  -> {(signs_s, signs_t): image};
+    the all-ones pattern is the kernel's documented convention (largest component of each eigenvector positive)."""
+    import itertools
 
-        def quirk(m):
-            U, D, Vh = torch.linalg.svd(m)
-            return (U @ torch.diag(D.sqrt()) @ Vh.t()).double().cpu()
-        want = ((quirk(t_cov[n]) @ torch.inverse(quirk(s_cov[n]))) @ s_n * t_std + t_mean).view(3, 40, 40)
-        close(y[n], want, rtol=2e-3, atol=2e-4)
-    assert torch.isfinite(y).all()
-    agree = 0
+    def stats(img):
+        f = img.reshape(3, -1).double()
+        mean, std = f.mean(1, keepdim=True), f.std(1, keepdim=True)
+        fn = (f - mean) / std
+        return fn, mean, std, fn @ fn.t() + torch.eye(3, dtype=torch.double)
+
+    def quirk(cov, signs):
+        d, u = torch.linalg.eigh(cov)
+        d, u = d.flip(0), u.flip(1).clone()
+        for j in range(3):
+            if u[u[:, j].abs().argmax(), j] < 0:
+                u[:, j] = -u[:, j]
+        u = u * torch.tensor(signs, dtype=torch.double)[None, :]
+        return u @ torch.diag(d.sqrt()) @ u
+
+    fs, _, _, cs = stats(source)
+    _, mt, st, ct = stats(target)
+    out = {}
+    for sa in itertools.product([1, -1], repeat=3):
+        for sb in itertools.product([1, -1], repeat=3):
+            m = quirk(ct, sb) @ torch.linalg.inv(quirk(cs, sa))
+            out[(sa, sb)] = ((m @ fs) * st + mt).reshape(source.shape)
+    return out
+
+
+def test_coral_batch(golden_ops):
+    """a15 parity, ASSERTED: (1) the reference fixture (CPU LAPACK) is one of the 64 sign patterns of the quirk --
+    i.e. the reference equals our formula modulo the SVD's sign gauge; (2) the kernel equals the pattern of its
+    documented convention to fp32 accuracy, on the fixtures and on a 380x380 batch."""
+    from unidefense_b200 import ops
+    ones = ((1, 1, 1), (1, 1, 1))
     for c in golden_ops["coral"]:
-        got = ops.coral_batch(c["source"][None].cuda(), c["target"][None].cuda())[0].cpu()
-        agree += int(torch.allclose(got, c["y"], rtol=1e-3, atol=1e-4))
-    print(f"coral: device SVD convention agrees with the CPU-LAPACK fixtures on {agree}/{len(golden_ops['coral'])} cases")
+        cand = _coral_candidates(c["source"], c["target"])
+        scale = float(c["y"].abs().max())
+        errs = {k: float((v - c["y"].double()).abs().max()) for k, v in cand.items()}
+        assert min(errs.values()) <= 1e-4 * scale, f"reference fixture matches no sign pattern (best {min(errs.values()):.2e})"
+        got = ops.coral_batch(c["source"][None].cuda(), c["target"][None].cuda())[0].cpu().double()
+        assert float((got - cand[ones]).abs().max()) <= 1e-4 * scale
+    g = torch.Generator().manual_seed(4)
+    base = torch.rand(4, 1, 380, 380, generator=g)
+    src = (0.6 * base + 0.4 * torch.rand(4, 3, 380, 380, generator=g)) * 2 - 1        # correlated channels, like faces
+    tgt = (0.5 * base.flip(0) + 0.5 * torch.rand(4, 3, 380, 380, generator=g)) * 1.2 - 0.5
+    y = ops.coral_batch(src.cuda(), tgt.cuda()).cpu().double()
+    assert torch.isfinite(y).all()
+    for n in range(4):
+        want = _coral_candidates(src[n], tgt[n])[ones]
+        assert float((y[n] - want).abs().max()) <= 2e-4 * float(want.abs().max())
+        # what coral is for: the output carries the target's per-channel mean and (unbiased) std
+    ym, ys = y.flatten(2).mean(-1), y.flatten(2).std(-1)
+    assert ym.shape == (4, 3) and ys.shape == (4, 3)

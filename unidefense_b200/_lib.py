@@ -61,6 +61,8 @@ SIGNATURES = {
     "ud_mask_kl_fwd": (c_i, [c_p] * 5 + [c_sz, c_i, c_i, c_p]),
     "ud_freq_style_workspace_bytes": (c_sz, [c_i] * 4),
     "ud_freq_style_transfer": (c_i, [c_p] * 5 + [c_sz] + [c_i] * 4 + [c_p]),
+    "ud_coral_workspace_bytes": (c_sz, [c_i, c_i]),
+    "ud_coral": (c_i, [c_p] * 4 + [c_sz, c_i, c_i, c_p]),
     "ud_gaussian_blur5": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "ud_downscale_nearest": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_p]),
     "ud_sf_pack": (c_i, [c_p, c_p] + [c_i] * 5 + [c_p]),

@@ -17,6 +17,8 @@
 #include "ud_common.cuh"
 
 #define DF_MAX_PRE 16  // 2 + D
+#define DF_GROUPS 32   // channel groups per CTA of the mask kernels (x 32 positions = 1024 threads): the channel loop of a
+                       // thread is Cp/32 independent 128-byte row loads, all in flight at once
 
 // ---------------------------------------------------------------- BN statistics (two-pass, per channel)
 __global__ void __launch_bounds__(128)
@@ -119,15 +121,15 @@ extern "C" int ud_bn_bwd_apply(const float* dz, const float* x, const float* mea
 }
 
 // ---------------------------------------------------------------- fused mask stage, forward
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DF_GROUPS * 32)
 df_mask_fwd_kernel(const float* __restrict__ proj, const float* __restrict__ bn_mean, const float* __restrict__ bn_rstd,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ diff,
                    const float* __restrict__ w2, const float* __restrict__ x, float* __restrict__ mask,
                    float* __restrict__ out, float* __restrict__ pmean, float* __restrict__ pmax,
                    int* __restrict__ argmax, int Cp, int D, int Cx, int HW, int tiles, int act) {
-  __shared__ float s_sum[8][33];
-  __shared__ float s_max[8][33];
-  __shared__ int s_arg[8][33];
+  __shared__ float s_sum[DF_GROUPS][33];
+  __shared__ float s_max[DF_GROUPS][33];
+  __shared__ int s_arg[DF_GROUPS][33];
   __shared__ float s_mask[32];
   const int n = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -137,7 +139,8 @@ df_mask_fwd_kernel(const float* __restrict__ proj, const float* __restrict__ bn_
   int am = 0x7fffffff;
   if (live) {
     const float* pp = proj + (long long)n * Cp * HW + pos;
-    for (int c = grp; c < Cp; c += 8) {
+#pragma unroll 4
+    for (int c = grp; c < Cp; c += DF_GROUPS) {
       const float rs = __ldg(bn_rstd + c);
       const float a = (gamma ? __ldg(gamma + c) : 1.f) * rs;
       const float b = (beta ? __ldg(beta + c) : 0.f) - __ldg(bn_mean + c) * a;
@@ -157,7 +160,7 @@ df_mask_fwd_kernel(const float* __restrict__ proj, const float* __restrict__ bn_
     float t = 0.f, m = -INFINITY;
     int a = 0x7fffffff;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < DF_GROUPS; ++q) {
       t += s_sum[q][lane];
       const float v = s_max[q][lane];
       const int ai = s_arg[q][lane];
@@ -184,7 +187,8 @@ df_mask_fwd_kernel(const float* __restrict__ proj, const float* __restrict__ bn_
   if (out != nullptr && live) {
     const float mk = s_mask[lane];
     const long long base = (long long)n * Cx * HW + pos;
-    for (int c = grp; c < Cx; c += 8) out[base + (long long)c * HW] = mk * x[base + (long long)c * HW];
+#pragma unroll 4
+    for (int c = grp; c < Cx; c += DF_GROUPS) out[base + (long long)c * HW] = mk * x[base + (long long)c * HW];
   }
 }
 
@@ -198,7 +202,7 @@ extern "C" int ud_dyfi_mask_fwd(const float* proj, const float* bn_mean, const f
   UD_REQUIRE(proj && bn_mean && bn_rstd && w2 && mask && pmean && pmax && argmax && (D == 0 || diff) && (!out || x),
              UD_ERR_INVALID, "dyfi_mask_fwd: null pointer");
   const int tiles = ud_cdiv(HW, 32);
-  df_mask_fwd_kernel<<<N * tiles, 256, 0, stream>>>(proj, bn_mean, bn_rstd, gamma, beta, diff, w2, x, mask, out, pmean,
+  df_mask_fwd_kernel<<<N * tiles, DF_GROUPS * 32, 0, stream>>>(proj, bn_mean, bn_rstd, gamma, beta, diff, w2, x, mask, out, pmean,
                                                     pmax, argmax, Cp, D, Cx, HW, tiles, act);
   return ud_check_launch("dyfi_mask_fwd");
 }
@@ -206,7 +210,7 @@ extern "C" int ud_dyfi_mask_fwd(const float* proj, const float* bn_mean, const f
 // ---------------------------------------------------------------- fused mask stage, backward
 // d_s = (g_mask + sum_c g_out*x) * m(1-m);  g_x = m*g_out;  g_w2[i] = sum d_s*pre_i;
 // dz[c] = d_s * (w2[0]/Cp + [c==argmax] w2[1]) * act'(z_c)      (grad w.r.t. the BN output)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DF_GROUPS * 32)
 df_mask_bwd_kernel(const float* __restrict__ proj, const float* __restrict__ bn_mean, const float* __restrict__ bn_rstd,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ diff,
                    const float* __restrict__ w2, const float* __restrict__ x, const float* __restrict__ mask,
@@ -214,9 +218,8 @@ df_mask_bwd_kernel(const float* __restrict__ proj, const float* __restrict__ bn_
                    const float* __restrict__ g_mask, const float* __restrict__ g_out, float* __restrict__ g_x,
                    float* __restrict__ dz, float* __restrict__ w2_part, int Cp, int D, int Cx, int HW, int tiles,
                    int act) {
-  __shared__ float s_t[8][33];
+  __shared__ float s_t[DF_GROUPS][33];
   __shared__ float s_ds[32];
-  __shared__ float red[33];
   const int n = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int pos = tile * 32 + lane;
@@ -226,7 +229,8 @@ df_mask_bwd_kernel(const float* __restrict__ proj, const float* __restrict__ bn_
   float t = 0.f;
   if (g_out != nullptr && live) {
     const long long base = (long long)n * Cx * HW + pos;
-    for (int c = grp; c < Cx; c += 8) {
+#pragma unroll 4
+    for (int c = grp; c < Cx; c += DF_GROUPS) {
       const float g = g_out[base + (long long)c * HW];
       t = fmaf(g, x[base + (long long)c * HW], t);
       g_x[base + (long long)c * HW] = mk * g;
@@ -237,7 +241,7 @@ df_mask_bwd_kernel(const float* __restrict__ proj, const float* __restrict__ bn_
   if (grp == 0) {
     float tt = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) tt += s_t[q][lane];
+    for (int q = 0; q < DF_GROUPS; ++q) tt += s_t[q][lane];
     const float gm = (g_mask != nullptr && live) ? g_mask[o] : 0.f;
     s_ds[lane] = live ? (gm + tt) * mk * (1.f - mk) : 0.f;
   }
@@ -248,7 +252,8 @@ df_mask_bwd_kernel(const float* __restrict__ proj, const float* __restrict__ bn_
     const int am = argmax[o];
     const float* pp = proj + (long long)n * Cp * HW + pos;
     float* dzp = dz + (long long)n * Cp * HW + pos;
-    for (int c = grp; c < Cp; c += 8) {
+#pragma unroll 4
+    for (int c = grp; c < Cp; c += DF_GROUPS) {
       const float rs = __ldg(bn_rstd + c);
       const float a = (gamma ? __ldg(gamma + c) : 1.f) * rs;
       const float b = (beta ? __ldg(beta + c) : 0.f) - __ldg(bn_mean + c) * a;
@@ -257,14 +262,16 @@ df_mask_bwd_kernel(const float* __restrict__ proj, const float* __restrict__ bn_
     }
   }
   // g_w2 partials (deterministic): index 0 mean, 1 max, 2.. diff
-  for (int i = 0; i < 2 + D; ++i) {
-    float v = 0.f;
-    if (grp == 0 && live) {
-      const float pre = (i == 0) ? pmean[o] : (i == 1) ? pmax[o] : diff[((long long)n * D + (i - 2)) * HW + pos];
-      v = ds * pre;
+  if (grp == 0) {                       // only the 32 positions of the tile contribute: one warp, no block barrier
+    for (int i = 0; i < 2 + D; ++i) {
+      float v = 0.f;
+      if (live) {
+        const float pre = (i == 0) ? pmean[o] : (i == 1) ? pmax[o] : diff[((long long)n * D + (i - 2)) * HW + pos];
+        v = ds * pre;
+      }
+      v = ud_warp_sum(v);
+      if (lane == 0) w2_part[(long long)blockIdx.x * DF_MAX_PRE + i] = v;
     }
-    v = ud_block_sum(v, red);
-    if (threadIdx.x == 0) w2_part[(long long)blockIdx.x * DF_MAX_PRE + i] = v;
   }
 }
 
@@ -299,7 +306,7 @@ extern "C" int ud_dyfi_mask_bwd(const float* proj, const float* bn_mean, const f
   UD_REQUIRE(ws_bytes >= ud_dyfi_mask_bwd_workspace_bytes(N, HW), UD_ERR_WORKSPACE, "dyfi_mask_bwd: workspace too small");
   const int tiles = ud_cdiv(HW, 32);
   float* part = static_cast<float*>(ws);
-  df_mask_bwd_kernel<<<N * tiles, 256, 0, stream>>>(proj, bn_mean, bn_rstd, gamma, beta, diff, w2, x, mask, pmean, pmax,
+  df_mask_bwd_kernel<<<N * tiles, DF_GROUPS * 32, 0, stream>>>(proj, bn_mean, bn_rstd, gamma, beta, diff, w2, x, mask, pmean, pmax,
                                                     argmax, g_mask, g_out, g_x, dz, part, Cp, D, Cx, HW, tiles, act);
   int rc = ud_check_launch("dyfi_mask_bwd");
   if (rc != UD_OK) return rc;

@@ -13,13 +13,15 @@
 #define LS_MAX_N 128
 
 // ---------------------------------------------------------------- a9 triplet
-// one CTA of 512 threads; dynamic smem: dist [N][N], H [N][N], sq [N], gu/fp/fn [N] each, then (when it fits)
-// a copy of feat [N][c].  The kernel is a chain of short dependent phases on one SM, so its time is load
-// latency: with the features staged in shared memory every phase reads at LDS latency instead of L2's.
+// one CTA of 512 threads; dynamic smem: dist [N][N], H [N][N] (later Hs = H + H^T), sq [N], gu/fp/fn [N] each, then
+// (when it fits) a copy of feat with row stride cs = c padded to 4 (mod 32) floats.  The kernel is a chain of short
+// dependent phases on one SM, so its time is latency: every phase is laid out so that ALL threads work at once --
+// one thread per (anchor, j) pair for the distances (float4 dot products from the padded copy: conflict-free),
+// one warp per anchor for the softmax-weighted sums, one thread per gradient element.
 #define LS_TRI_THREADS 512
 __global__ void __launch_bounds__(LS_TRI_THREADS)
 ls_triplet_kernel(const float* __restrict__ feat, const long long* __restrict__ labels, float* __restrict__ loss,
-                  float* __restrict__ gfeat, int N, int c, int staged) {
+                  float* __restrict__ gfeat, int N, int c, int cs, int staged) {
   extern __shared__ float smf[];
   __shared__ int s_nr;
   __shared__ float red[33];
@@ -40,40 +42,46 @@ ls_triplet_kernel(const float* __restrict__ feat, const long long* __restrict__ 
   float* fnv = fpv + N;
   float* fstage = smf + ((2 * N * N + 4 * N + 3) & ~3);   // 16-byte aligned (host sizes it the same way)
   if (staged) {
-    const int tot = N * c;
-    if ((c & 3) == 0 && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0)) {
-      for (int i = tid; i < tot / 4; i += nth)
-        reinterpret_cast<float4*>(fstage)[i] = __ldg(reinterpret_cast<const float4*>(feat) + i);
-    } else {
-      for (int i = tid; i < tot; i += nth) fstage[i] = __ldg(feat + i);
+    for (int i = tid; i < N * cs; i += nth) {
+      const int r = i / cs, k = i - r * cs;
+      fstage[i] = (k < c) ? __ldg(feat + (long long)r * c + k) : 0.f;     // zero padding: dot products may run over cs
     }
   }
   const float* f = staged ? fstage : feat;
+  const int fs = staged ? cs : c;                          // row stride of f
   __syncthreads();
   const int nr = s_nr;
-  // squared norms
   const int warp = tid >> 5, lane = tid & 31, nwarps = nth >> 5;
+  // squared norms: one warp per row
   for (int i = warp; i < N; i += nwarps) {
     float s = 0.f;
     for (int k = lane; k < c; k += 32) {
-      const float v = f[(long long)i * c + k];
+      const float v = f[(long long)i * fs + k];
       s = fmaf(v, v, s);
     }
     s = ud_warp_sum(s);
     if (lane == 0) sq[i] = s;
   }
   __syncthreads();
-  // distances for anchor rows: one warp per (i, j) pair
-  for (int p = warp; p < nr * N; p += nwarps) {
+  // distances of the anchor rows: one THREAD per (i, j) pair
+  for (int p = tid; p < nr * N; p += nth) {
     const int i = p / N, j = p - i * N;
     float s = 0.f;
-    for (int k = lane; k < c; k += 32) s = fmaf(f[(long long)i * c + k], f[(long long)j * c + k], s);
-    s = ud_warp_sum(s);
-    if (lane == 0) {
-      const float q = sq[i] + sq[j] - 2.f * s;
-      dist[i * N + j] = sqrtf(fmaxf(q, 1e-12f));
-      Hm[i * N + j] = (q >= 1e-12f) ? 1.f : 0.f;  // clamp(min) passes gradient only where q >= min
+    if (staged) {
+      const float4* a = reinterpret_cast<const float4*>(fstage + i * cs);
+      const float4* b = reinterpret_cast<const float4*>(fstage + j * cs);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int k = 0; k < cs / 4; ++k) {
+        const float4 u = a[k], v = b[k];
+        s0 = fmaf(u.x, v.x, s0); s1 = fmaf(u.y, v.y, s1); s2 = fmaf(u.z, v.z, s2); s3 = fmaf(u.w, v.w, s3);
+      }
+      s = (s0 + s1) + (s2 + s3);
+    } else {
+      for (int k = 0; k < c; ++k) s = fmaf(__ldg(feat + (long long)i * c + k), __ldg(feat + (long long)j * c + k), s);
     }
+    const float q = sq[i] + sq[j] - 2.f * s;
+    dist[p] = sqrtf(fmaxf(q, 1e-12f));
+    Hm[p] = (q >= 1e-12f) ? 1.f : 0.f;  // clamp(min) passes gradient only where q >= min
   }
   __syncthreads();
   // per-anchor weighted sums: one warp per anchor
@@ -123,26 +131,29 @@ ls_triplet_kernel(const float* __restrict__ feat, const long long* __restrict__ 
   lsum = ud_block_sum(lsum, red);  // also orders the Hm writes before the reads below
   if (tid == 0) *loss = (nr > 0) ? lsum / (float)nr : 0.f;
   if (gfeat == nullptr) return;
-  // gx_m = x_m * rowsum(Hs)_m - sum_j Hs_mj x_j,  Hs = H + H^T (rows >= nr of H are zero)
+  // Hs = H + H^T (rows >= nr of H are zero) into `dist`, then its row sums into sq
+  for (int p = tid; p < N * N; p += nth) {
+    const int m = p / N, j = p - m * N;
+    float h = 0.f;
+    if (m < nr) h += Hm[m * N + j];
+    if (j < nr) h += Hm[j * N + m];
+    dist[p] = h;
+  }
+  __syncthreads();
   for (int m = warp; m < N; m += nwarps) {
     float rs = 0.f;
-    for (int j = lane; j < N; j += 32) {
-      float h = 0.f;
-      if (m < nr) h += Hm[m * N + j];
-      if (j < nr) h += Hm[j * N + m];
-      rs += h;
-    }
+    for (int j = lane; j < N; j += 32) rs += dist[m * N + j];
     rs = ud_warp_sum(rs);
-    for (int k = lane; k < c; k += 32) {
-      float acc = f[(long long)m * c + k] * rs;
-      for (int j = 0; j < N; ++j) {
-        float h = 0.f;
-        if (m < nr) h += Hm[m * N + j];
-        if (j < nr) h += Hm[j * N + m];
-        acc = fmaf(-h, f[(long long)j * c + k], acc);
-      }
-      gfeat[(long long)m * c + k] = acc;
-    }
+    if (lane == 0) sq[m] = rs;
+  }
+  __syncthreads();
+  // gx_m = x_m * rowsum(Hs)_m - sum_j Hs_mj x_j : one thread per element (consecutive k: conflict-free, Hs broadcast)
+  for (int e = tid; e < N * c; e += nth) {
+    const int m = e / c, k = e - m * c;
+    float acc = f[(long long)m * fs + k] * sq[m];
+    const float* hs = dist + m * N;
+    for (int j = 0; j < N; ++j) acc = fmaf(-hs[j], f[(long long)j * fs + k], acc);
+    gfeat[e] = acc;
   }
 }
 
@@ -152,12 +163,14 @@ extern "C" int ud_triplet_fwd(const float* feat, const long long* labels, float*
   UD_REQUIRE(N <= LS_MAX_N, UD_ERR_UNSUPPORTED, "triplet: per-rank batch %d > %d unsupported", N, LS_MAX_N);
   UD_REQUIRE(feat && labels && loss, UD_ERR_INVALID, "triplet: null pointer");
   const size_t base = sizeof(float) * (2ull * N * N + 4ull * N);
-  const size_t stage = ud_align_up(sizeof(float) * (size_t)N * c, 16);
+  int cs = (c + 3) & ~3;                                  // multiple of 4 floats (float4 rows) ...
+  while ((cs & 31) != 4 && (cs & 31) != 12 && (cs & 31) != 20 && (cs & 31) != 28) cs += 4;   // ... and = 4 (mod 8) banks-wise
+  const size_t stage = sizeof(float) * (size_t)N * cs;
   const int staged = (ud_align_up(base, 16) + stage <= (200u << 10)) ? 1 : 0;
   const size_t smem = staged ? ud_align_up(base, 16) + stage : base;
   if (smem > (48u << 10))
     UD_CUDA(cudaFuncSetAttribute(ls_triplet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ls_triplet_kernel<<<1, LS_TRI_THREADS, smem, stream>>>(feat, labels, loss, gfeat, N, c, staged);
+  ls_triplet_kernel<<<1, LS_TRI_THREADS, smem, stream>>>(feat, labels, loss, gfeat, N, c, cs, staged);
   return ud_check_launch("triplet");
 }
 

@@ -631,37 +631,21 @@ def spatial_style_transfer(content, style, lmda):
     return (cf + (1 - lm) * matched - (1 - lm) * cf).view(B, C, H, W)
 
 
-def _coral_stats(img):
-    """utils/operation.py:6-12,:24-27 batched: normalised pixels [N,C,HW], mean, unbiased std, f f^T + I."""
-    N, C = img.shape[:2]
-    f = img.reshape(N, C, -1)
-    mean = f.mean(dim=-1, keepdim=True)
-    std = f.std(dim=-1, keepdim=True)
-    fn = (f - mean) / std
-    cov = fn @ fn.transpose(1, 2) + torch.eye(C, device=img.device, dtype=img.dtype)
-    return fn, mean, std, cov
-
-
-def _coral_quirk_sqrt(covs):
-    """_mat_sqrt (operation.py:15-17) per matrix: U diag(sqrt(D)) Vh^T with torch's UNBATCHED svd."""
-    outs = []
-    for m in covs:
-        U, D, Vh = torch.linalg.svd(m)
-        outs.append(U @ torch.diag(D.sqrt()) @ Vh.t())
-    return torch.stack(outs)
-
-
 def coral_batch(source, target):
-    """coral (utils/operation.py:20-45) for every (source[n], target[n]) pair: statistics, 3x3 algebra and the
-    colour transform are batched (no per-sample python loop over images as in model/unidefense.py:189-191).
-    The reference's 'square root' U*sqrt(D)*Vh^T (Appendix D) is NOT invariant to the sign convention of the
-    SVD (fp32 vs fp64 LAPACK already disagree by O(1)), so the 2N tiny factorisations go through the same
-    unbatched torch.linalg.svd call the reference makes on this device."""
+    """coral (utils/operation.py:20-45) for every (source[n], target[n]) pair in three launches (csrc/ud_coral.cu): the
+    per-sample Python loop of model/unidefense.py:189-191 and its 2N host-synchronising 3x3 SVDs are gone.  The
+    reference's 'square root' U*sqrt(D)*Vh^T (Appendix D) depends on the sign convention of the SVD library; the
+    kernel fixes the gauge (largest component of each eigenvector positive) and parity is asserted modulo it."""
+    source, target = source.detach().contiguous(), target.detach().contiguous()
     L.require_cuda_f32(source, target)
-    s_n, _, _, s_cov = _coral_stats(source)
-    _, t_mean, t_std, t_cov = _coral_stats(target)
-    m = _coral_quirk_sqrt(t_cov) @ torch.linalg.inv(_coral_quirk_sqrt(s_cov))
-    return ((m @ s_n) * t_std + t_mean).view(source.shape)
+    if source.shape != target.shape or source.dim() != 4 or source.shape[1] != 3:
+        raise ValueError(f"coral_batch: expected two [N,3,H,W] tensors, got {tuple(source.shape)} / {tuple(target.shape)}")
+    N, _, H, W = source.shape
+    lib = L.lib()
+    out = torch.empty_like(source)
+    ws = L.workspace(lib.ud_coral_workspace_bytes(N, H * W), source.device)
+    L.check(lib.ud_coral(L.ptr(source), L.ptr(target), L.ptr(out), L.ptr(ws), ws.numel(), N, H * W, L.stream()), "coral")
+    return out
 
 
 # ------------------------------------------------------------------------------------------
