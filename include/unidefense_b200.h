@@ -149,6 +149,17 @@ UD_API int ud_proj_prep_w(const float* w, float* hi, float* lo, int Cout, int Ci
 UD_API int ud_proj_fwd(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, float* y,
                        float* part_mean, float* part_m2, float* part_cnt, int N, int H, int W, int Cin, int Cout,
                        int ksize, cudaStream_t stream);
+/* Backward of the projections on the same tensor-core kernel:
+ *   data gradient   dX = conv(dY, flip(W)^T): ud_proj_fwd with x = dY (channels-last) and the weights re-laid by
+ *                   ud_proj_prep_wt ([Cout,Cin,k,k] -> [Cin, k*k flipped, Cout]); output lands NCHW like the forward.
+ *   weight gradient (1x1) dW[co,ci] = sum_{n,p} dY[n,co,p] X[n,ci,p]: ud_proj_wgrad_1x1, both operands NCHW [N,C,P],
+ *                   K = (sample, 32-pixel chunk) via 3-D TMA boxes; P % 4 == 0.  (The 3x3 weight gradient stays on
+ *                   the library: its K blocks are not 128-byte rows for 12x12 / 24x24 planes.)
+ *   ud_proj_split: elementwise hi/lo split of an operand for 3xTF32.                                              */
+UD_API int ud_proj_prep_wt(const float* w, float* hi, float* lo, int Cout, int Cin, int taps, cudaStream_t stream);
+UD_API int ud_proj_split(const float* x, float* hi, float* lo, long long total, cudaStream_t stream);
+UD_API int ud_proj_wgrad_1x1(const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* dw,
+                             int N, int P, int Cin, int Cout, cudaStream_t stream);
 UD_API int ud_bn_merge_partials(const float* part_mean, const float* part_m2, const float* part_cnt, float* mean,
                                 float* m2, int tiles, int C, cudaStream_t stream);
 /* Everything after layer1's conv: BN-apply + act + channel mean/max + cat(diff) + conv1x1 (w2 [2+D]) +
@@ -186,6 +197,14 @@ UD_API int ud_mask_kl_fwd(const float* pred, const float* gt, float* loss, float
  * signature: both arguments are log-probabilities [N,M] (workspace: ud_mask_kl_workspace_bytes).  */
 UD_API int ud_kl_div_log_target_fwd(const float* log_pred, const float* log_target, float* loss, float* g_pred,
                                     void* ws, size_t ws_bytes, int N, int M, cudaStream_t stream);
+
+/* ---- a12: classification loss (engine/abstract_engine.py:256-259, :325-328) ------------------------------------
+ * nn.CrossEntropyLoss() on logits [N,K] / int64 targets [N] (mean reduction), and the num_classes == 1 branch
+ * nn.BCEWithLogitsLoss() on logits [N] / float targets [N].  g_logits (nullable) = d loss / d logits.            */
+UD_API int ud_cross_entropy_fwd(const float* logits, const long long* target, float* loss, float* g_logits, int N,
+                                int K, cudaStream_t stream);
+UD_API int ud_bce_with_logits_fwd(const float* logits, const float* target, float* loss, float* g_logits, int N,
+                                  cudaStream_t stream);
 
 /* ---- a13: FrequencyStyleTransfer (model/modules.py:35-55; no grad) --------------------------------------
  * out = irfft2((lmda*|Fa| + (1-lmda)*|Fb|) * exp(1j*angle(Fa))), Fa/Fb = rfft2 of content/style, ortho;

@@ -1,6 +1,7 @@
 """a9-a11 parity: fused triplet / factorization / mask-KL losses (value + gradient)."""
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import recon_path as O
 
@@ -101,3 +102,28 @@ def test_mask_kl_vs_oracle(shape):
     l64.backward()
     close(l, l64, rtol=1e-3, atol=1e-7)
     close(pc.grad, p64.grad, rtol=1e-3, atol=1e-7)
+
+
+def test_cross_entropy_and_bce_match_torch():
+    """a12: the engine's two classification-loss branches (engine/abstract_engine.py:256-259)."""
+    from unidefense_b200.loss import get_loss
+    g = torch.Generator().manual_seed(3)
+    for N, K in [(4, 2), (32, 2), (7, 5), (64, 2)]:
+        z = (torch.randn(N, K, generator=g) * 3).cuda().requires_grad_()
+        t = torch.randint(0, K, (N,), generator=g).cuda()
+        loss = get_loss("cross_entropy", "cuda")(z, t)
+        (gz,) = torch.autograd.grad(loss * 1.7, [z])
+        z64 = z.detach().double().cpu().requires_grad_()
+        ref = F.cross_entropy(z64, t.cpu())
+        (gr,) = torch.autograd.grad(ref * 1.7, [z64])
+        torch.testing.assert_close(loss.double().cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(gz.double().cpu(), gr, rtol=1e-4, atol=1e-7)
+        zb = (torch.randn(N, generator=g) * 4).cuda().requires_grad_()
+        tb = torch.randint(0, 2, (N,), generator=g).float().cuda()
+        lb = get_loss("bce", "cuda")(zb, tb)
+        (gb,) = torch.autograd.grad(lb, [zb])
+        zb64 = zb.detach().double().cpu().requires_grad_()
+        rb = F.binary_cross_entropy_with_logits(zb64, tb.double().cpu())
+        (grb,) = torch.autograd.grad(rb, [zb64])
+        torch.testing.assert_close(lb.double().cpu(), rb.detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(gb.double().cpu(), grb, rtol=1e-4, atol=1e-7)

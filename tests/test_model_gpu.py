@@ -162,3 +162,54 @@ def test_eval_mode_and_dtypes():
     assert torch.isfinite(torch.softmax(out["cls_out"], 1)).all()
     out2 = model(x)
     torch.testing.assert_close(out2["cls_out"], out["cls_out"])      # deterministic
+
+
+# bf16 statement for the BENCHMARKED configuration (bench.py: bf16 autocast for the stock-torch backbone and the dense
+# convolutions, channels_last backbone, SFConv transforms as bf16 DFT-by-GEMM, TF32 tcgen05 projections, fp32 hot-path
+# kernels) against the fp32 reference fixtures.  bf16 carries 8 mantissa bits (2^-9 = 2e-3 per rounding); through the
+# 32-block EfficientNet-B4 with train-mode BatchNorm on 4 samples the observed drift is a few 1e-2 relative, hence:
+#   per-sample losses / triplet features / loss: |err| <= 6e-2 * max|ref|     masks, rec (bounded by 1): <= 6e-2 abs
+#   logits: <= 0.15 * max|ref| + 0.1 (the head sits behind every bf16 layer).
+BF16_REL, BF16_MASK_ABS = 6e-2, 6e-2
+
+
+@pytest.mark.parametrize("arch", ["eb4", "r18"])
+def test_bench_configuration_bf16_against_fp32_reference(arch, no_dropout):
+    from unidefense_b200 import ops
+    fix = torch.load(os.path.join(GOLDEN, f"full_{arch}.pt"), weights_only=False)
+    model = _build(arch, 5, False)
+    for part in ("backbone", "extractor", "emb_block1", "emb_block2"):      # bench.py --channels-last backbone
+        if hasattr(model, part):
+            getattr(model, part).to(memory_format=torch.channels_last)
+    x = P.tensor_for(f"in:full_x_{arch}", (fix["N"], 3, fix["R"], fix["R"]), "unit").cuda()
+    labels = fix["labels"].cuda()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True                                   # torch default, as in bench.py
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ld = out["loss_dict"]
+
+    def near(a, b, what, rel=BF16_REL, floor=0.0):
+        b = b.detach().float()
+        tol = rel * max(float(b.abs().max()), 1e-6) + floor
+        err = float((a.detach().float().cpu() - b).abs().max())
+        assert err <= tol, f"{what}: max abs err {err:.3e} > {tol:.3e} (bf16 bench configuration)"
+
+    near(ld["spatial"], fix["spatial"], "spatial")
+    near(ld["freq"], fix["freq"], "freq")
+    near(ld["freq_mask"], fix["freq_mask"], "freq_mask", 0.0, BF16_MASK_ABS)
+    near(ld["spat_mask"], fix["spat_mask"], "spat_mask", 0.0, BF16_MASK_ABS)
+    near(out["rec"][:, :, ::7, ::5], fix["rec_sample"], "rec", 0.0, BF16_MASK_ABS)
+    for i, (a, b) in enumerate(zip(ld["triplet"], fix["triplet_feats"])):
+        near(a, b, f"triplet[{i}]")
+    near(out["cls_out"], fix["cls_out"], "cls_out", 0.15, 0.1)
+    nr = fix["N"] // 2
+    tri = sum(ops.triplet_loss(f.float(), labels) for f in ld["triplet"])
+    loss = (ops.cross_entropy(out["cls_out"].float(), labels) + 0.1 * ld["freq_mask"].mean() + 0.1 * ld["spat_mask"].mean()
+            + 0.1 * tri + 0.1 * ld["spatial"][:nr].mean() + 1.0 * ld["freq"][:nr].mean())
+    near(loss, fix["loss"], "loss")
+    loss.backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.requires_grad)

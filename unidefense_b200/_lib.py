@@ -50,6 +50,9 @@ SIGNATURES = {
     "ud_proj_prep_x": (c_i, [c_p] * 3 + [c_i] * 3 + [c_p]),
     "ud_proj_prep_w": (c_i, [c_p] * 3 + [c_i] * 3 + [c_p]),
     "ud_proj_fwd": (c_i, [c_p] * 8 + [c_i] * 6 + [c_p]),
+    "ud_proj_prep_wt": (c_i, [c_p] * 3 + [c_i] * 3 + [c_p]),
+    "ud_proj_split": (c_i, [c_p] * 3 + [ctypes.c_longlong, c_p]),
+    "ud_proj_wgrad_1x1": (c_i, [c_p] * 5 + [c_i] * 4 + [c_p]),
     "ud_bn_merge_partials": (c_i, [c_p] * 5 + [c_i] * 2 + [c_p]),
     "ud_dyfi_mask_fwd": (c_i, [c_p] * 13 + [c_i] * 6 + [c_p]),
     "ud_dyfi_mask_bwd_workspace_bytes": (c_sz, [c_i, c_i]),
@@ -61,6 +64,8 @@ SIGNATURES = {
     "ud_mask_kl_fwd": (c_i, [c_p] * 5 + [c_sz, c_i, c_i, c_p]),
     "ud_freq_style_workspace_bytes": (c_sz, [c_i] * 4),
     "ud_freq_style_transfer": (c_i, [c_p] * 5 + [c_sz] + [c_i] * 4 + [c_p]),
+    "ud_cross_entropy_fwd": (c_i, [c_p] * 4 + [c_i, c_i, c_p]),
+    "ud_bce_with_logits_fwd": (c_i, [c_p] * 4 + [c_i, c_p]),
     "ud_coral_workspace_bytes": (c_sz, [c_i, c_i]),
     "ud_coral": (c_i, [c_p] * 4 + [c_sz, c_i, c_i, c_p]),
     "ud_gaussian_blur5": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),

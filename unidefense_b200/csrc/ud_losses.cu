@@ -463,3 +463,59 @@ extern "C" int ud_kl_div_log_target_fwd(const float* log_pred, const float* log_
   ls_sum_kernel<<<1, 128, 0, stream>>>(rows, loss, N);
   return ud_check_launch("kl_div_sum");
 }
+
+// ---------------------------------------------------------------- a12 classification loss
+// nn.CrossEntropyLoss() (mean over the batch) on logits [N,K] with int64 targets, and nn.BCEWithLogitsLoss() on
+// logits [N] with float targets -- the two branches of engine/abstract_engine.py:256-259 / :325-328.  One CTA:
+// value and d loss / d logits in the same pass (the head is [N,2] or [N]: latency, not bandwidth).
+__global__ void __launch_bounds__(128)
+ls_ce_kernel(const float* __restrict__ logits, const long long* __restrict__ target, float* __restrict__ loss,
+             float* __restrict__ g, int N, int K) {
+  __shared__ float red[33];
+  float l = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float* z = logits + (long long)n * K;
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) m = fmaxf(m, z[k]);
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += expf(z[k] - m);
+    const float lse = m + logf(s);
+    const int t = (int)target[n];
+    l += lse - z[t];
+    if (g) {
+      for (int k = 0; k < K; ++k) g[(long long)n * K + k] = (expf(z[k] - lse) - (k == t ? 1.f : 0.f)) / (float)N;
+    }
+  }
+  l = ud_block_sum(l, red);
+  if (threadIdx.x == 0) *loss = l / (float)N;
+}
+
+__global__ void __launch_bounds__(128)
+ls_bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ target, float* __restrict__ loss,
+                     float* __restrict__ g, int N) {
+  __shared__ float red[33];
+  float l = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float z = logits[n], t = target[n];
+    l += fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));          // torch's stable form
+    if (g) g[n] = (1.f / (1.f + expf(-z)) - t) / (float)N;
+  }
+  l = ud_block_sum(l, red);
+  if (threadIdx.x == 0) *loss = l / (float)N;
+}
+
+extern "C" int ud_cross_entropy_fwd(const float* logits, const long long* target, float* loss, float* g_logits, int N,
+                                    int K, cudaStream_t stream) {
+  UD_REQUIRE(N >= 1 && K >= 1, UD_ERR_INVALID, "cross_entropy: bad shape N=%d K=%d", N, K);
+  UD_REQUIRE(logits && target && loss, UD_ERR_INVALID, "cross_entropy: null pointer");
+  ls_ce_kernel<<<1, 128, 0, stream>>>(logits, target, loss, g_logits, N, K);
+  return ud_check_launch("cross_entropy");
+}
+
+extern "C" int ud_bce_with_logits_fwd(const float* logits, const float* target, float* loss, float* g_logits, int N,
+                                      cudaStream_t stream) {
+  UD_REQUIRE(N >= 1, UD_ERR_INVALID, "bce_with_logits: bad shape N=%d", N);
+  UD_REQUIRE(logits && target && loss, UD_ERR_INVALID, "bce_with_logits: null pointer");
+  ls_bce_logits_kernel<<<1, 128, 0, stream>>>(logits, target, loss, g_logits, N);
+  return ud_check_launch("bce_with_logits");
+}

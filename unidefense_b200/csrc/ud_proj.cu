@@ -20,6 +20,7 @@
 //     pixels -- two-pass inside the tile, merged across tiles with Chan's formula by ud_bn_merge_partials.
 //     The separate full read of `proj` by ud_bn_stats disappears.
 #include <cuda.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -47,6 +48,9 @@ struct PjGeom {
   int tiles_per_sample;           // 4-D, bn == 1: ceil(H / bh)
   int m_tiles, n_tiles, kc;       // kc = ceil(Cin / 32) k-blocks per tap
   int a_rows, b_rows;             // rows the A / B boxes really carry (<= 128): the TMA transaction size
+  int wgrad;                      // 1: weight-gradient GEMM of the 1x1 projection (see ud_proj_wgrad_1x1): A and B are both
+                                  // NCHW activations [n][channel][pixel], K runs over (sample, 32-pixel chunk)
+  int kp;                         // wgrad: 32-pixel chunks per sample = ceil(P / 32)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -72,6 +76,10 @@ __device__ __forceinline__ void pj_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void pj_tma_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
                    "r"(pj_smem(dst)), "l"(map), "r"(pj_smem(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void pj_tma_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+                   "r"(pj_smem(dst)), "l"(map), "r"(pj_smem(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void pj_tma_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
@@ -108,6 +116,13 @@ __device__ __forceinline__ void pj_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
 // tile row r -> (sample, pixel) of the output it produces; false for padding rows of the tile
 __device__ __forceinline__ bool pj_row(const PjGeom& g, int m_tile, int r, int& n, int& p) {
   const int P = g.H * g.W;
+  if (g.wgrad) {                   // D'[ci, co]: "pixel" = ci of a single pseudo-sample with P = Cin rows
+    const int m = m_tile * PJ_BLOCK_M + r;
+    if (m >= g.H) return false;
+    n = 0;
+    p = m;
+    return true;
+  }
   if (g.flat) {
     const long long m = (long long)m_tile * PJ_BLOCK_M + r;
     if (m >= (long long)g.N * P) return false;
@@ -147,7 +162,7 @@ pj_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-  const int num_kb = g.taps * g.kc;
+  const int num_kb = g.wgrad ? g.N * g.kp : g.taps * g.kc;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PJ_STAGES; ++s) {
@@ -186,6 +201,12 @@ pj_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const CUtensorMap* ma = o ? &map_a_lo : &map_a_hi;
         const CUtensorMap* mb = o ? &map_b_lo : &map_b_hi;
         uint8_t* sa = st + o * (PJ_A_BYTES + PJ_B_BYTES);
+        if (g.wgrad) {             // K block = 32 pixels of sample smp; rows = channels (pixels beyond P: zero fill)
+          const int smp = kb / g.kp, p0 = (kb - smp * g.kp) * PJ_BLOCK_K;
+          pj_tma_3d(sa, ma, full + s, p0, m_tile * PJ_BLOCK_M, smp);
+          pj_tma_3d(sa + PJ_A_BYTES, mb, full + s, p0, n_tile * PJ_BLOCK_N, smp);
+          continue;
+        }
         if (g.flat) pj_tma_2d(sa, ma, full + s, c0, m_tile * PJ_BLOCK_M);
         else pj_tma_4d(sa, ma, full + s, c0, dx, h0 + dy, n0);
         pj_tma_2d(sa + PJ_A_BYTES, mb, full + s, tap * g.Cin + c0, n_tile * PJ_BLOCK_N);
@@ -400,6 +421,8 @@ static int pj_geometry(int N, int H, int W, int Cin, int Cout, int ksize, PjGeom
   g->kc = ud_cdiv(Cin, PJ_BLOCK_K);
   g->n_tiles = ud_cdiv(Cout, PJ_BLOCK_N);
   g->flat = (ksize == 1);
+  g->wgrad = 0;
+  g->kp = 0;
   g->bh = g->bn = g->tiles_per_sample = 1;
   if (g->flat) {
     g->m_tiles = ud_cdiv((long long)N * H * W, PJ_BLOCK_M);
@@ -491,6 +514,97 @@ extern "C" int ud_proj_fwd(const float* x_hi, const float* x_lo, const float* w_
     pj_gemm_kernel<false><<<grid, PJ_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, y, part_mean, part_m2, part_cnt, g);
   }
   return ud_check_launch("pj_gemm");
+}
+
+// ---- backward of the projections ------------------------------------------------------------------------
+// elementwise hi/lo split (no re-layout): the NCHW operands of the weight-gradient GEMM in 3xTF32
+__global__ void pj_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __ldg(x + i), h = pj_tf32_hi(v);
+    hi[i] = h;
+    lo[i] = pj_tf32_hi(v - h);
+  }
+}
+
+// w [Cout, Cin, k, k] -> wt [Cin, k*k, Cout] with the taps FLIPPED: the weights of the data-gradient convolution
+// dX = conv(dY, flip(W)^T), an implicit GEMM of the same form as the forward one.
+__global__ void pj_prep_wt_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long total,
+                                  int Cout, int Cin, int T) {
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const long long ci = o / ((long long)T * Cout);
+    const int rem = (int)(o - ci * T * Cout);
+    const int t = rem / Cout, co = rem - t * Cout;
+    const float v = __ldg(w + ((long long)co * Cin + ci) * T + (T - 1 - t));
+    if (lo != nullptr) {
+      const float h = pj_tf32_hi(v);
+      hi[o] = h;
+      lo[o] = pj_tf32_hi(v - h);
+    } else {
+      hi[o] = pj_tf32_hi(v);
+    }
+  }
+}
+
+extern "C" int ud_proj_split(const float* x, float* hi, float* lo, long long total, cudaStream_t stream) {
+  UD_REQUIRE(x && hi && lo && total >= 1, UD_ERR_INVALID, "proj_split: bad arguments");
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  pj_split_kernel<<<blocks, 256, 0, stream>>>(x, hi, lo, total);
+  return ud_check_launch("pj_split");
+}
+
+extern "C" int ud_proj_prep_wt(const float* w, float* hi, float* lo, int Cout, int Cin, int taps, cudaStream_t stream) {
+  UD_REQUIRE(w && hi && Cout >= 1 && Cin >= 1 && taps >= 1, UD_ERR_INVALID, "proj_prep_wt: bad arguments");
+  const long long total = (long long)Cout * Cin * taps;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  pj_prep_wt_kernel<<<blocks, 256, 0, stream>>>(w, hi, lo, total, Cout, Cin, taps);
+  return ud_check_launch("pj_prep_wt");
+}
+
+// Weight gradient of the 1x1 projection: dw [Cout, Cin] = sum_{n,p} dy[n,co,p] * x[n,ci,p], both operands NCHW
+// ([N, C, P], P = h*w pixels, P % 4 == 0).  D'[ci, co] is accumulated over K = (sample, 32-pixel chunk) blocks fetched
+// by 3-D TMA boxes {32 pixels, 128 channels, 1 sample} (pixels beyond P are zero-filled) and the epilogue's
+// column-major store lands it as dw[co][ci].  x_lo / dy_lo: nullable 3xTF32 low parts (ud_proj_split).
+extern "C" int ud_proj_wgrad_1x1(const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* dw,
+                                 int N, int P, int Cin, int Cout, cudaStream_t stream) {
+  UD_REQUIRE(N >= 1 && P >= 1 && Cin >= 1 && Cout >= 1, UD_ERR_INVALID, "proj_wgrad: bad shape");
+  UD_REQUIRE(P % 4 == 0, UD_ERR_UNSUPPORTED, "proj_wgrad: P=%d pixels per plane must be a multiple of 4 (TMA row pitch)", P);
+  UD_REQUIRE(x_hi && dy_hi && dw, UD_ERR_INVALID, "proj_wgrad: null pointer");
+  UD_REQUIRE((x_lo == nullptr) == (dy_lo == nullptr), UD_ERR_INVALID, "proj_wgrad: x_lo and dy_lo go together (3xTF32)");
+  PjGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = N; g.H = Cin; g.W = 1; g.Cin = P; g.Cout = Cout; g.taps = 1; g.flat = 0; g.wgrad = 1;
+  g.bh = g.bn = g.tiles_per_sample = 1;
+  g.kp = ud_cdiv(P, PJ_BLOCK_K);
+  g.kc = g.kp;
+  g.m_tiles = ud_cdiv(Cin, PJ_BLOCK_M);
+  g.n_tiles = ud_cdiv(Cout, PJ_BLOCK_N);
+  g.a_rows = Cin < PJ_BLOCK_M ? Cin : PJ_BLOCK_M;
+  g.b_rows = Cout < PJ_BLOCK_N ? Cout : PJ_BLOCK_N;
+  const bool split = x_lo != nullptr;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  for (int o = 0; o < (split ? 2 : 1); ++o) {
+    cuuint64_t da[3] = {(cuuint64_t)P, (cuuint64_t)Cin, (cuuint64_t)N};
+    cuuint64_t sa[2] = {(cuuint64_t)P * 4, (cuuint64_t)Cin * P * 4};
+    cuuint32_t ba[3] = {PJ_BLOCK_K, (cuuint32_t)g.a_rows, 1};
+    if ((rc = pj_make_map(o ? &ma_lo : &ma_hi, o ? x_lo : x_hi, 3, da, sa, ba)) != UD_OK) return rc;
+    cuuint64_t db[3] = {(cuuint64_t)P, (cuuint64_t)Cout, (cuuint64_t)N};
+    cuuint64_t sb[2] = {(cuuint64_t)P * 4, (cuuint64_t)Cout * P * 4};
+    cuuint32_t bb[3] = {PJ_BLOCK_K, (cuuint32_t)g.b_rows, 1};
+    if ((rc = pj_make_map(o ? &mb_lo : &mb_hi, o ? dy_lo : dy_hi, 3, db, sb, bb)) != UD_OK) return rc;
+  }
+  if (!split) { ma_lo = ma_hi; mb_lo = mb_hi; }
+  const size_t stage = (size_t)(split ? 2 : 1) * (PJ_A_BYTES + PJ_B_BYTES);
+  const size_t smem = 1024 + PJ_STAGES * stage + 128;
+  dim3 grid(g.n_tiles, g.m_tiles);
+  if (split) {
+    UD_CUDA(cudaFuncSetAttribute(pj_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pj_gemm_kernel<true><<<grid, PJ_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, dw, nullptr, nullptr, nullptr, g);
+  } else {
+    UD_CUDA(cudaFuncSetAttribute(pj_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pj_gemm_kernel<false><<<grid, PJ_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, dw, nullptr, nullptr, nullptr, g);
+  }
+  return ud_check_launch("pj_wgrad");
 }
 
 extern "C" int ud_bn_merge_partials(const float* part_mean, const float* part_m2, const float* part_cnt, float* mean,

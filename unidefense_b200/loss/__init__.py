@@ -34,11 +34,31 @@ class KLDivLogTarget(nn.Module):
         return ops.kl_div_log_target(log_pred.float(), log_target.float())
 
 
+class CrossEntropyLoss(nn.Module):
+    """nn.CrossEntropyLoss() (loss/__init__.py:14) for the engine's call `softmax(cls_out, in_tgt)`
+    (engine/abstract_engine.py:259): class-index targets, mean reduction; soft targets / weights / label smoothing are
+    not on the reference path and go to torch."""
+
+    def forward(self, logits, target):
+        if logits.is_cuda and logits.dim() == 2 and target.dtype == torch.int64 and target.dim() == 1:
+            return ops.cross_entropy(logits, target)
+        return nn.functional.cross_entropy(logits, target)
+
+
+class BCEWithLogitsLoss(nn.Module):
+    """nn.BCEWithLogitsLoss() (loss/__init__.py:12), the num_classes == 1 branch (engine/abstract_engine.py:257)."""
+
+    def forward(self, logits, target):
+        if logits.is_cuda and logits.shape == target.shape:
+            return ops.bce_with_logits(logits, target)
+        return nn.functional.binary_cross_entropy_with_logits(logits, target)
+
+
 LOSSES = {
     "mse": nn.MSELoss(),
-    "bce": nn.BCEWithLogitsLoss(),
+    "bce": BCEWithLogitsLoss(),
     "factorization": FactorizationLoss(),
-    "cross_entropy": nn.CrossEntropyLoss(),
+    "cross_entropy": CrossEntropyLoss(),
     "aw_triplet": AsymmetricalWeightedTripletLoss(),
     "kl_div": KLDivLogTarget(),
 }

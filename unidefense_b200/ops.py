@@ -381,15 +381,51 @@ class _ProjConv(torch.autograd.Function):
             ctx.mark_non_differentiable(mean, m2)
         ctx.save_for_backward(x, weight)
         ctx.k = k
+        ctx.split = split
         return y, mean, m2
 
     @staticmethod
     def backward(ctx, gy, _gm, _g2):
+        """Data gradient (1x1 and 3x3) and the 1x1 weight gradient on the same tcgen05 kernel; the 3x3 weight gradient
+        (and shapes outside the kernel's limits) through the library's convolution_backward."""
         x, weight = ctx.saved_tensors
-        k = ctx.k
-        gx, gw, _ = torch.ops.aten.convolution_backward(
-            gy.contiguous(), x, weight, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
-            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        k, split = ctx.k, ctx.split
+        N, Cin, H, W = x.shape
+        Cout = weight.shape[0]
+        lib = L.lib()
+        dev = x.device
+        gy = gy.contiguous()
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gx = gw = None
+        if need_x and Cout % 4 == 0 and Cout >= 32:
+            g_hi = torch.empty(N, H, W, Cout, device=dev, dtype=torch.float32)
+            g_lo = torch.empty_like(g_hi) if split else None
+            L.check(lib.ud_proj_prep_x(L.ptr(gy), L.ptr(g_hi), L.ptr(g_lo), N, Cout, H * W, L.stream()), "proj_prep_x")
+            wc = weight.contiguous()
+            wt_hi = torch.empty(Cin, k * k, Cout, device=dev, dtype=torch.float32)
+            wt_lo = torch.empty_like(wt_hi) if split else None
+            L.check(lib.ud_proj_prep_wt(L.ptr(wc), L.ptr(wt_hi), L.ptr(wt_lo), Cout, Cin, k * k, L.stream()), "proj_prep_w")
+            gx = torch.empty(N, Cin, H, W, device=dev, dtype=torch.float32)
+            L.check(lib.ud_proj_fwd(L.ptr(g_hi), L.ptr(g_lo), L.ptr(wt_hi), L.ptr(wt_lo), L.ptr(gx), None, None, None,
+                                    N, H, W, Cout, Cin, k, L.stream()), "proj_dgrad")
+            need_x = False
+        if need_w and k == 1 and (H * W) % 4 == 0:
+            xc = x.contiguous()
+            if split:
+                x_hi, x_lo, d_hi, d_lo = (torch.empty_like(xc), torch.empty_like(xc), torch.empty_like(gy), torch.empty_like(gy))
+                L.check(lib.ud_proj_split(L.ptr(xc), L.ptr(x_hi), L.ptr(x_lo), xc.numel(), L.stream()), "proj_prep_x")
+                L.check(lib.ud_proj_split(L.ptr(gy), L.ptr(d_hi), L.ptr(d_lo), gy.numel(), L.stream()), "proj_prep_x")
+            else:
+                x_hi, x_lo, d_hi, d_lo = xc, None, gy, None
+            gw = torch.empty(Cout, Cin, 1, 1, device=dev, dtype=torch.float32)
+            L.check(lib.ud_proj_wgrad_1x1(L.ptr(x_hi), L.ptr(x_lo), L.ptr(d_hi), L.ptr(d_lo), L.ptr(gw), N, H * W, Cin, Cout,
+                                          L.stream()), "proj_wgrad")
+            need_w = False
+        if need_x or need_w:
+            ax, aw, _ = torch.ops.aten.convolution_backward(gy, x, weight, None, [1, 1], [k // 2, k // 2], [1, 1], False,
+                                                            [0, 0], 1, [need_x, need_w, False])
+            gx = ax if need_x else gx
+            gw = aw if need_w else gw
         return gx, gw, None, None
 
 
@@ -575,6 +611,44 @@ def mask_kl_loss(mask_pred, mask_gt):
 def kl_div_log_target(log_pred, log_target):
     """nn.KLDivLoss(reduction='batchmean', log_target=True)(log_pred, log_target) for [N, M] inputs."""
     return _MaskKL.apply(log_pred, log_target, False)
+
+
+class _CrossEntropy(torch.autograd.Function):
+    """nn.CrossEntropyLoss() / nn.BCEWithLogitsLoss() as the engine calls them (engine/abstract_engine.py:256-259)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, binary):
+        logits = logits.contiguous()
+        L.require_cuda_f32(logits)
+        loss = torch.empty((), device=logits.device, dtype=torch.float32)
+        g = torch.empty_like(logits) if ctx.needs_input_grad[0] else None
+        lib = L.lib()
+        if binary:
+            t = target.detach().to(torch.float32).contiguous()
+            if t.shape != logits.shape:
+                raise ValueError(f"bce_with_logits: logits {tuple(logits.shape)} vs target {tuple(t.shape)}")
+            L.check(lib.ud_bce_with_logits_fwd(L.ptr(logits), L.ptr(t), L.ptr(loss), L.ptr(g), logits.numel(), L.stream()),
+                    "bce_with_logits")
+        else:
+            if target.dtype != torch.int64 or not target.is_cuda or logits.dim() != 2 or target.numel() != logits.shape[0]:
+                raise RuntimeError("cross_entropy: logits [N,K] fp32 and CUDA int64 class targets [N] expected")
+            L.check(lib.ud_cross_entropy_fwd(L.ptr(logits), L.ptr(target.contiguous()), L.ptr(loss), L.ptr(g),
+                                             logits.shape[0], logits.shape[1], L.stream()), "cross_entropy")
+        ctx.save_for_backward(g)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        (g,) = ctx.saved_tensors
+        return g * gl, None, None
+
+
+def cross_entropy(logits, target):
+    return _CrossEntropy.apply(logits.float(), target, False)
+
+
+def bce_with_logits(logits, target):
+    return _CrossEntropy.apply(logits.float(), target, True)
 
 
 # ------------------------------------------------------------------------------------------
