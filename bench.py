@@ -734,15 +734,23 @@ def run_ours(args):
         flush.zero_()
         eager_step(x_dev, l_dev)
     try:
-        prof = cupti_kernel_times(_prof_step, prof_steps)
+        if rank == 0:
+            prof = cupti_kernel_times(_prof_step, prof_steps)
+        else:                                # the other ranks only keep the collectives of those steps company
+            prof = {}
+            for _ in range(prof_steps):
+                _prof_step()
+            torch.cuda.synchronize()
         prof_how = "CUPTI kernel records (torch.profiler) of the step re-issued eagerly after the timed region"
     except Exception as e:                   # noqa: BLE001
-        L.PROFILE = {}
-        for _ in range(prof_steps):
-            _prof_step()
-        torch.cuda.synchronize()
-        prof = L.profile_summary()
-        L.PROFILE = None
+        prof = {}
+        if world == 1:                       # (at N>1 extra steps on one rank would unbalance the collectives)
+            L.PROFILE = {}
+            for _ in range(prof_steps):
+                _prof_step()
+            torch.cuda.synchronize()
+            prof = L.profile_summary()
+            L.PROFILE = None
         prof_how = f"CUDA events around each C-ABI call (CUPTI unavailable: {type(e).__name__})"
 
     # end to end through the public API with HOST buffers: pinned H2D of the batch + D2H of the loss every step

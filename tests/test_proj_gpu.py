@@ -46,19 +46,33 @@ def test_conv_and_stats(case, precision, layout):
         torch.testing.assert_close(m2.double().cpu(), r2, rtol=stol, atol=stol * float(r2.abs().max()))
 
 
-def test_gradients_match_convolution_backward():
+# (N, Cin, Cout, H, W, k): 1x1 -> data AND weight gradient on tcgen05; 3x3 -> data gradient on tcgen05, weight gradient
+# through the library; ragged channel counts; a plane whose pixel count is not a multiple of 32 (K padding of wgrad)
+GRAD_CASES = [(3, 64, 96, 8, 5, 1), (4, 544, 544, 12, 7, 1), (2, 100, 36, 6, 6, 1), (3, 64, 80, 8, 8, 3),
+              (2, 272, 272, 12, 12, 3), (1, 48, 40, 24, 24, 3)]
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+def test_gradients_match_convolution_backward(case, precision):
+    from unidefense_b200 import _lib as L
     from unidefense_b200 import ops
-    g = torch.Generator().manual_seed(5)
-    x = torch.randn(3, 64, 8, 8, generator=g)
-    w = torch.randn(80, 64, 3, 3, generator=g) * 0.05
-    gy = torch.randn(3, 80, 8, 8, generator=g)
+    N, Cin, Cout, H, W, k = case
+    g = torch.Generator().manual_seed(5 + Cin + Cout + k)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    gy = torch.randn(N, Cout, H, W, generator=g)
     xd, wd = x.cuda().requires_grad_(), w.cuda().requires_grad_()
-    y, _, _ = ops.proj_conv(xd, wd, "3xtf32")
+    y, _, _ = ops.proj_conv(xd, wd, precision)
+    before = L.lib().ud_launch_count()
     gx, gw = torch.autograd.grad((y * gy.cuda()).sum(), [xd, wd])
+    launched = L.lib().ud_launch_count() - before
+    assert launched >= (4 if k == 1 else 3)          # prep + tcgen05 GEMM(s) really ran in backward
     x64, w64 = x.double().requires_grad_(), w.double().requires_grad_()
-    rx, rw = torch.autograd.grad((F.conv2d(x64, w64, None, 1, 1) * gy.double()).sum(), [x64, w64])
-    torch.testing.assert_close(gx.double().cpu(), rx, rtol=1e-4, atol=1e-5 * float(rx.abs().max()))
-    torch.testing.assert_close(gw.double().cpu(), rw, rtol=1e-4, atol=1e-5 * float(rw.abs().max()))
+    rx, rw = torch.autograd.grad((F.conv2d(x64, w64, None, 1, k // 2) * gy.double()).sum(), [x64, w64])
+    tol = 3e-5 if precision == "3xtf32" else 5e-3
+    assert float((gx.double().cpu() - rx).abs().max()) <= tol * float(rx.abs().max())
+    assert float((gw.double().cpu() - rw).abs().max()) <= tol * float(rw.abs().max())
 
 
 def test_filter_modules_use_the_tensor_core_path(golden_ops_r2):

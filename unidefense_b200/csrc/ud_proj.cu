@@ -567,7 +567,8 @@ extern "C" int ud_proj_prep_wt(const float* w, float* hi, float* lo, int Cout, i
 extern "C" int ud_proj_wgrad_1x1(const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* dw,
                                  int N, int P, int Cin, int Cout, cudaStream_t stream) {
   UD_REQUIRE(N >= 1 && P >= 1 && Cin >= 1 && Cout >= 1, UD_ERR_INVALID, "proj_wgrad: bad shape");
-  UD_REQUIRE(P % 4 == 0, UD_ERR_UNSUPPORTED, "proj_wgrad: P=%d pixels per plane must be a multiple of 4 (TMA row pitch)", P);
+  UD_REQUIRE(P % 4 == 0 && P >= PJ_BLOCK_K, UD_ERR_UNSUPPORTED,
+             "proj_wgrad: P=%d pixels per plane must be a multiple of 4 (TMA row pitch) and >= %d", P, PJ_BLOCK_K);
   UD_REQUIRE(x_hi && dy_hi && dw, UD_ERR_INVALID, "proj_wgrad: null pointer");
   UD_REQUIRE((x_lo == nullptr) == (dy_lo == nullptr), UD_ERR_INVALID, "proj_wgrad: x_lo and dy_lo go together (3xTF32)");
   PjGeom g;

@@ -409,7 +409,7 @@ class _ProjConv(torch.autograd.Function):
             L.check(lib.ud_proj_fwd(L.ptr(g_hi), L.ptr(g_lo), L.ptr(wt_hi), L.ptr(wt_lo), L.ptr(gx), None, None, None,
                                     N, H, W, Cout, Cin, k, L.stream()), "proj_dgrad")
             need_x = False
-        if need_w and k == 1 and (H * W) % 4 == 0:
+        if need_w and k == 1 and (H * W) % 4 == 0 and H * W >= 32:
             xc = x.contiguous()
             if split:
                 x_hi, x_lo, d_hi, d_lo = (torch.empty_like(xc), torch.empty_like(xc), torch.empty_like(gy), torch.empty_like(gy))
