@@ -52,8 +52,10 @@ UD_API const char* ud_last_error(void);
 UD_API int ud_version(void);
 /* Kernels launched by this library since load (process-wide, monotonic): bench.py's gpu_launches. */
 UD_API long long ud_launch_count(void);
-/* 1 when n-point line FFTs are supported (prime factors <= 23, n <= UD_FFT_MAX_N). */
+/* 1 when n-point line FFTs run on the mixed-radix plan (prime factors <= 23, n <= UD_FFT_MAX_N);
+ * ud_fft_size_any: 1 for every 1 <= n <= UD_FFT_MAX_N (other sizes run Bluestein's algorithm). */
 UD_API int ud_fft_size_supported(int n);
+UD_API int ud_fft_size_any(int n);
 
 /* ---- a1: reconstruction-loss tail --------------------------------------------------------
  * Replaces model/unidefense.py:244-253 (Eb4), :423-433 (Res18), :618-628 (Res50):
@@ -114,6 +116,16 @@ UD_API int ud_rfft2_cat(const float* x, float* xf, int N, int C, int h, int w, i
  * rfft2's backward (fft_r2c_backward: zero-padded half spectrum, no mirroring).    */
 UD_API int ud_irfft2_cat(const float* xf, const float* mask, float* y, int N, int C, int h, int w, int norm_ortho,
                          int adjoint_of_forward, cudaStream_t stream);
+/* Generic forms of the two calls above for ANY 1 <= h, w <= UD_FFT_MAX_N (torch.fft.rfft2 / irfft2 as called at
+ * model/unidefense.py:135-145, :246-249, model/modules.py:43-54, model/efficientnet/exp.py:55-65,
+ * model/resnet/exp.py:44-54): mixed radix when every prime factor is <= 23, Bluestein otherwise.  Planes with
+ * h, w <= 64 take the workspace-free small-plane path; larger planes need ws of ud_rfft2_workspace_bytes()
+ * (the row-transformed half spectrum, [N*C][h][w/2+1] complex).  Same flags and layouts as the _cat calls.  */
+UD_API size_t ud_rfft2_workspace_bytes(int N, int C, int h, int w);
+UD_API int ud_rfft2(const float* x, float* xf, void* ws, size_t ws_bytes, int N, int C, int h, int w, int norm_ortho,
+                    int adjoint_of_inverse, cudaStream_t stream);
+UD_API int ud_irfft2(const float* xf, const float* mask, float* y, void* ws, size_t ws_bytes, int N, int C, int h,
+                     int w, int norm_ortho, int adjoint_of_forward, cudaStream_t stream);
 /* out = (1-s)*smask*emb + s*ff + res, s = sigmoid(*fuse_coef) (model/unidefense.py:153-155).
  * emb, ff, res, out [N,C,HW]; smask [N,HW]; res = dropout(emb.clone()) or NULL (= emb).             */
 UD_API int ud_attn_fuse_fwd(const float* emb, const float* smask, const float* ff, const float* res,
@@ -213,6 +225,14 @@ UD_API size_t ud_freq_style_workspace_bytes(int N, int C, int H, int W);
 UD_API int ud_freq_style_transfer(const float* content, const float* style, const float* lmda, float* out, void* ws,
                                   size_t ws_bytes, int N, int C, int H, int W, cudaStream_t stream);
 
+/* a14 -- SpatialStyleTransfer (model/modules.py:59-76; no grad): exact rank matching per (n,c) plane,
+ *   out = content + (1-lmda[n]) * style_sorted[rank(content)] - (1-lmda[n]) * content
+ * content, style, out [N,C,HW]; lmda [N].  One stable radix sort per plane (style: keys only; content: keys + pixel
+ * index with the blend fused into the last pass) through ws of ud_spatial_style_workspace_bytes().  Replaces the
+ * reference's two torch.sort + argsort + gather.  Ties keep pixel order (torch.sort leaves it unspecified).   */
+UD_API size_t ud_spatial_style_workspace_bytes(int N, int C, int HW);
+UD_API int ud_spatial_style_transfer(const float* content, const float* style, const float* lmda, float* out, void* ws,
+                                     size_t ws_bytes, int N, int C, int HW, cudaStream_t stream);
 /* ---- a15: coral colour-statistics transfer (utils/operation.py:15-45; model/unidefense.py:189-191; no grad) ---------
  * source[n] takes the per-channel mean / unbiased std and the 3x3 "f f^T + I" colour structure of target[n]:
  *   out = sqrt~(cov_t) inv(sqrt~(cov_s)) (s - mean_s)/std_s * std_t + mean_t,  sqrt~(M) = U sqrt(D) Vh^T (the

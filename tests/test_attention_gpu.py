@@ -38,6 +38,10 @@ def test_bilinear_fwd_bwd(shape, size):
 
 
 SIZES = [(12, 12), (8, 8), (16, 16), (24, 24), (7, 7), (5, 6), (9, 4), (19, 19), (1, 1), (2, 3), (48, 48), (64, 64), (3, 64)]
+# two-kernel path through the workspace (a side > 64): mixed radix (95 = 5*19, 380, 150, 75), Bluestein (74 = 2*37,
+# 62 = 2*31, 124, 67 prime, 248 = 8*31), odd / even widths, degenerate sides, non-square
+SIZES += [(95, 95), (65, 65), (380, 380), (150, 75), (74, 74), (62, 124), (67, 3), (3, 67), (1, 100), (100, 1), (248, 96),
+          (128, 80)]
 
 
 @pytest.mark.parametrize("hw", SIZES)
@@ -46,7 +50,7 @@ def test_rfft2_irfft2_fwd_bwd(hw, norm):
     from unidefense_b200 import ops
     h, w = hw
     g = torch.Generator().manual_seed(h * 100 + w)
-    N, C = 2, 5
+    N, C = (2, 5) if h * w < 50000 else (1, 2)
     x = torch.randn(N, C, h, w, generator=g)
     wgt = torch.randn(N, 2 * C, h, w // 2 + 1, generator=g)
     xc = x.cuda().requires_grad_()
@@ -90,7 +94,7 @@ def test_rfft2_config_shapes_roundtrip():
 def test_unsupported_and_empty():
     from unidefense_b200 import ops
     with pytest.raises(RuntimeError):
-        ops.rfft2_cat(torch.zeros(1, 1, 65, 65, device="cuda"))
+        ops.rfft2_cat(torch.zeros(1, 1, 1025, 8, device="cuda"))       # > UD_FFT_MAX_N
     assert ops.rfft2_cat(torch.zeros(0, 4, 8, 8, device="cuda")).shape == (0, 8, 8, 5)
     with pytest.raises(ValueError):
         ops.irfft2_cat(torch.zeros(1, 4, 8, 4, device="cuda"), (8, 8))

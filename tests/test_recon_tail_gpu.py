@@ -21,6 +21,10 @@ SHAPES = [
     (1, 3, 150, 150, 299, 299),  # 13*23
     (2, 3, 192, 192, 380, 380),  # UDEB4 config (static plan 19*5*4)
     (1, 3, 200, 100, 50, 40),    # downsampling path of the transposed resize
+    (2, 3, 29, 29, 58, 58),      # 58 = 2*29: Bluestein (prime factor > 23) on both axes
+    (1, 2, 31, 40, 62, 80),      # Bluestein columns (62 = 2*31), mixed-radix rows
+    (1, 3, 124, 124, 248, 248),  # the ADVICE example: 248 = 8*31
+    (1, 1, 20, 37, 40, 37),      # prime 37 rows
 ]
 
 
@@ -111,7 +115,7 @@ def test_empty_and_errors():
     rec, sp, fr = ops.recon_tail(dec, x)
     assert rec.shape == (0, 3, 8, 8) and sp.numel() == 0 and fr.numel() == 0
     with pytest.raises(RuntimeError):
-        ops.recon_tail(torch.zeros(1, 3, 29, 29, device="cuda"), torch.zeros(1, 3, 58, 58, device="cuda"))  # 29 > 23
+        ops.recon_tail(torch.zeros(1, 1, 8, 8, device="cuda"), torch.zeros(1, 1, 8, 1025, device="cuda"))   # > UD_FFT_MAX_N
     with pytest.raises(RuntimeError):
         ops.recon_tail(torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 8, 8))  # CPU tensors: no fallback
 

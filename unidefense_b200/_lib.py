@@ -26,6 +26,7 @@ SIGNATURES = {
     "ud_version": (c_i, []),
     "ud_launch_count": (ctypes.c_longlong, []),
     "ud_fft_size_supported": (c_i, [c_i]),
+    "ud_fft_size_any": (c_i, [c_i]),
     "ud_recon_tail_workspace_bytes": (c_sz, [c_i] * 6),
     "ud_recon_tail_signs_bytes": (c_sz, [c_i] * 4),
     "ud_recon_tail_fwd": (c_i, [c_p] * 7 + [c_sz] + [c_i] * 7 + [c_p]),
@@ -40,6 +41,9 @@ SIGNATURES = {
     "ud_attn_prep": (c_i, [c_p] * 4 + [c_i] * 9 + [c_p]),
     "ud_rfft2_cat": (c_i, [c_p, c_p] + [c_i] * 6 + [c_p]),
     "ud_irfft2_cat": (c_i, [c_p, c_p, c_p] + [c_i] * 6 + [c_p]),
+    "ud_rfft2_workspace_bytes": (c_sz, [c_i] * 4),
+    "ud_rfft2": (c_i, [c_p] * 3 + [c_sz] + [c_i] * 6 + [c_p]),
+    "ud_irfft2": (c_i, [c_p] * 4 + [c_sz] + [c_i] * 6 + [c_p]),
     "ud_attn_fuse_fwd": (c_i, [c_p] * 6 + [c_i] * 3 + [c_p]),
     "ud_attn_fuse_bwd_workspace_bytes": (c_sz, [c_i, c_i]),
     "ud_attn_fuse_bwd": (c_i, [c_p] * 10 + [c_sz] + [c_i] * 4 + [c_p]),
@@ -66,6 +70,8 @@ SIGNATURES = {
     "ud_freq_style_transfer": (c_i, [c_p] * 5 + [c_sz] + [c_i] * 4 + [c_p]),
     "ud_cross_entropy_fwd": (c_i, [c_p] * 4 + [c_i, c_i, c_p]),
     "ud_bce_with_logits_fwd": (c_i, [c_p] * 4 + [c_i, c_p]),
+    "ud_spatial_style_workspace_bytes": (c_sz, [c_i] * 3),
+    "ud_spatial_style_transfer": (c_i, [c_p] * 5 + [c_sz] + [c_i] * 3 + [c_p]),
     "ud_coral_workspace_bytes": (c_sz, [c_i, c_i]),
     "ud_coral": (c_i, [c_p] * 4 + [c_sz, c_i, c_i, c_p]),
     "ud_gaussian_blur5": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),

@@ -12,6 +12,7 @@
 
 #include "../../include/unidefense_b200.h"
 #include "ud_fft.cuh"
+#include "ud_fft_any.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -69,6 +70,7 @@ extern "C" int ud_fft_size_supported(int n) {
   UdDynPlan p;
   return (n >= 1 && n <= UD_FFT_MAX_N && ud_make_dyn_plan(n, &p)) ? 1 : 0;
 }
+extern "C" int ud_fft_size_any(int n) { return (n >= 1 && n <= UD_FFT_MAX_N) ? 1 : 0; }
 
 // exp(-2 pi i t / n) with exact octant symmetry (so W^(n/4), W^(n/2) ... are exact)
 static void twiddle_host(int n, std::vector<float2>& out) {
@@ -208,4 +210,109 @@ const int2* ud_lerp_ranges(int in, int out) {
   }
   g_range_cache[key] = p;
   return p;
+}
+
+
+// ---- Bluestein tables (ud_fft_any.cuh) -------------------------------------------------------------
+struct BluesteinTables {
+  float2* chirp;
+  float2* bhat;
+};
+static std::map<std::pair<int, int>, BluesteinTables> g_bs_cache;
+
+// in-place radix-2 FFT in double precision (host, table construction only)
+static void host_fft_pow2(std::vector<double>& re, std::vector<double>& im) {
+  const size_t m = re.size();
+  for (size_t i = 1, j = 0; i < m; ++i) {
+    size_t bit = m >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) {
+      std::swap(re[i], re[j]);
+      std::swap(im[i], im[j]);
+    }
+  }
+  for (size_t len = 2; len <= m; len <<= 1) {
+    for (size_t i = 0; i < m; i += len) {
+      for (size_t k = 0; k < len / 2; ++k) {
+        const double ang = -2.0 * M_PI * (double)k / (double)len;
+        const double wr = cos(ang), wi = sin(ang);
+        const size_t a = i + k, b = i + k + len / 2;
+        const double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+        re[b] = re[a] - xr;
+        im[b] = im[a] - xi;
+        re[a] += xr;
+        im[a] += xi;
+      }
+    }
+  }
+}
+
+bool ud_make_any_plan(int n, UdAnyPlan* plan) {
+  if (n < 1 || n > UD_FFT_MAX_N) {
+    ud_set_error("FFT size %d outside [1, %d]", n, UD_FFT_MAX_N);
+    return false;
+  }
+  plan->n_ = n;
+  plan->chirp = nullptr;
+  plan->bhat = nullptr;
+  if (ud_make_dyn_plan(n, &plan->inner)) {
+    plan->m = n;
+    plan->bluestein = 0;
+    plan->tw = ud_twiddles(n);
+    return plan->tw != nullptr;
+  }
+  int m = 1;
+  while (m < 2 * n - 1) m <<= 1;
+  plan->m = m;
+  plan->bluestein = 1;
+  if (!ud_make_dyn_plan(m, &plan->inner)) {
+    ud_set_error("FFT size %d: no stage plan for the Bluestein length %d", n, m);
+    return false;
+  }
+  plan->tw = ud_twiddles(m);
+  if (!plan->tw) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    ud_set_error("cudaGetDevice failed");
+    return false;
+  }
+  std::lock_guard<std::mutex> lock(g_tw_mutex);
+  auto key = std::make_pair(dev, n);
+  auto it = g_bs_cache.find(key);
+  if (it == g_bs_cache.end()) {
+    std::vector<double> wr(n), wi(n), br(m, 0.0), bi(m, 0.0);
+    for (int j = 0; j < n; ++j) {
+      const long long q = ((long long)j * j) % (2LL * n);      // phase pi * j^2 / n reduced mod 2 pi
+      const double ang = M_PI * (double)q / (double)n;
+      wr[j] = cos(ang);
+      wi[j] = -sin(ang);                                       // w[j] = exp(-i pi j^2 / n)
+    }
+    for (int t = 0; t < n; ++t) {                              // conj(w), even in t, wrapped to length m
+      br[t] = wr[t];
+      bi[t] = -wi[t];
+      if (t) {
+        br[m - t] = wr[t];
+        bi[m - t] = -wi[t];
+      }
+    }
+    host_fft_pow2(br, bi);
+    std::vector<float2> hc(n), hb(m);
+    for (int j = 0; j < n; ++j) hc[j] = make_float2((float)wr[j], (float)wi[j]);
+    for (int k = 0; k < m; ++k) hb[k] = make_float2((float)(br[k] / m), (float)(bi[k] / m));
+    BluesteinTables t = {nullptr, nullptr};
+    if (cudaMalloc(&t.chirp, sizeof(float2) * (size_t)n) != cudaSuccess ||
+        cudaMalloc(&t.bhat, sizeof(float2) * (size_t)m) != cudaSuccess ||
+        cudaMemcpy(t.chirp, hc.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(t.bhat, hb.data(), sizeof(float2) * (size_t)m, cudaMemcpyHostToDevice) != cudaSuccess) {
+      ud_set_error("Bluestein tables for n=%d: allocation or copy failed", n);
+      if (t.chirp) cudaFree(t.chirp);
+      if (t.bhat) cudaFree(t.bhat);
+      return false;
+    }
+    it = g_bs_cache.emplace(key, t).first;
+  }
+  plan->chirp = it->second.chirp;
+  plan->bhat = it->second.bhat;
+  return true;
 }

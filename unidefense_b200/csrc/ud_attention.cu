@@ -251,7 +251,7 @@ at_c2r_kernel(const float* __restrict__ in, const float* __restrict__ mask, floa
 static int at_check_small(const char* what, int N, int C, int h, int w) {
   UD_REQUIRE(N >= 0 && C >= 1 && h >= 1 && w >= 1, UD_ERR_INVALID, "%s: bad shape N=%d C=%d h=%d w=%d", what, N, C, h, w);
   UD_REQUIRE(h <= AT_MAX_DIM && w <= AT_MAX_DIM, UD_ERR_UNSUPPORTED,
-             "%s: plane %dx%d exceeds the small-plane path (max %d); use ud_rfft2_large", what, h, w, AT_MAX_DIM);
+             "%s: plane %dx%d exceeds the small-plane path (max %d); use ud_rfft2 / ud_irfft2", what, h, w, AT_MAX_DIM);
   return UD_OK;
 }
 
@@ -273,12 +273,11 @@ static float at_scale(int h, int w, int norm_ortho, bool inverse) {
 }
 
 // mode 0: forward transform (scale per norm);  mode 1: adjoint of the inverse transform (irfft2 backward)
-extern "C" int ud_rfft2_cat(const float* x, float* xf, int N, int C, int h, int w, int norm_ortho, int adjoint_of_inverse,
-                            cudaStream_t stream) {
-  int rc = at_check_small("rfft2_cat", N, C, h, w);
-  if (rc != UD_OK) return rc;
-  if (N == 0) return UD_OK;
-  UD_REQUIRE(x && xf, UD_ERR_INVALID, "rfft2_cat: null pointer");
+bool ud_fft2_small_ok(int h, int w) { return h <= AT_MAX_DIM && w <= AT_MAX_DIM; }
+
+int ud_rfft2_small(const float* x, float* xf, int N, int C, int h, int w, int norm_ortho, int adjoint_of_inverse,
+                   cudaStream_t stream) {
+  int rc;
   const int P = at_planes_per_cta(h, w);
   const size_t smem = at_smem_bytes(h, w, P);
   if ((rc = at_set_smem(at_r2c_kernel, smem)) != UD_OK) return rc;
@@ -288,14 +287,20 @@ extern "C" int ud_rfft2_cat(const float* x, float* xf, int N, int C, int h, int 
   return ud_check_launch("rfft2_cat");
 }
 
-// mode 0: inverse transform irfft2(s=(h,w)) (column multipliers m_k, scale per norm);
-// mode 1: adjoint of the forward transform (rfft2 backward: zero-padded, no multipliers)
-extern "C" int ud_irfft2_cat(const float* xf, const float* mask, float* y, int N, int C, int h, int w, int norm_ortho,
-                             int adjoint_of_forward, cudaStream_t stream) {
-  int rc = at_check_small("irfft2_cat", N, C, h, w);
+extern "C" int ud_rfft2_cat(const float* x, float* xf, int N, int C, int h, int w, int norm_ortho, int adjoint_of_inverse,
+                            cudaStream_t stream) {
+  int rc = at_check_small("rfft2_cat", N, C, h, w);
   if (rc != UD_OK) return rc;
   if (N == 0) return UD_OK;
-  UD_REQUIRE(xf && y, UD_ERR_INVALID, "irfft2_cat: null pointer");
+  UD_REQUIRE(x && xf, UD_ERR_INVALID, "rfft2_cat: null pointer");
+  return ud_rfft2_small(x, xf, N, C, h, w, norm_ortho, adjoint_of_inverse, stream);
+}
+
+// mode 0: inverse transform irfft2(s=(h,w)) (column multipliers m_k, scale per norm);
+// mode 1: adjoint of the forward transform (rfft2 backward: zero-padded, no multipliers)
+int ud_irfft2_small(const float* xf, const float* mask, float* y, int N, int C, int h, int w, int norm_ortho,
+                    int adjoint_of_forward, cudaStream_t stream) {
+  int rc;
   const int P = at_planes_per_cta(h, w);
   const size_t smem = at_smem_bytes(h, w, P);
   if ((rc = at_set_smem(at_c2r_kernel, smem)) != UD_OK) return rc;
@@ -304,6 +309,15 @@ extern "C" int ud_irfft2_cat(const float* xf, const float* mask, float* y, int N
   at_c2r_kernel<<<ud_cdiv(planes, P), AT_THREADS, smem, stream>>>(xf, mask, y, planes, C, h, w, scale,
                                                                    adjoint_of_forward ? 0 : 1, P);
   return ud_check_launch("irfft2_cat");
+}
+
+extern "C" int ud_irfft2_cat(const float* xf, const float* mask, float* y, int N, int C, int h, int w, int norm_ortho,
+                             int adjoint_of_forward, cudaStream_t stream) {
+  int rc = at_check_small("irfft2_cat", N, C, h, w);
+  if (rc != UD_OK) return rc;
+  if (N == 0) return UD_OK;
+  UD_REQUIRE(xf && y, UD_ERR_INVALID, "irfft2_cat: null pointer");
+  return ud_irfft2_small(xf, mask, y, N, C, h, w, norm_ortho, adjoint_of_forward, stream);
 }
 
 // ---------------------------------------------------------------- a4: error maps

@@ -67,6 +67,20 @@ __device__ __forceinline__ float ud_block_sum(float v, float* red) {
 }
 
 __device__ __forceinline__ float ud_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
+// Flush-to-zero forms of the two special-function instructions (MUFU.EX2 / MUFU.RCP, <= 2 ulp): without .ftz the
+// compiler wraps each in a denormal range check + rescale (3-4 extra instructions), which made the issue-bound
+// epilogue kernels pay ~12 instructions per swish instead of 5.  A flushed denormal here is a sigmoid of |z| > 87.
+__device__ __forceinline__ float ud_ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ud_rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ud_sigmoid_fast(float x) { return ud_rcp_ftz(1.f + ud_ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float ud_sign(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
 // cp.async (LDGSTS): global -> shared without staging in registers, so a CTA can put its whole tile in

@@ -112,6 +112,7 @@ struct UdStaticPlan {
   static constexpr bool kInPlace = false;
   static constexpr int kN = N;
   __device__ __forceinline__ int n() const { return N; }
+  __device__ __forceinline__ int line_len() const { return N; }      // points a line buffer must hold
   // Runs all stages; data must be in `a` and visible (caller synced).  Returns the buffer
   // holding the result; ends with a __syncthreads().
   __device__ __forceinline__ float2* run(float2* a, float2* b, const float2* tw, int L, int LS) const {
@@ -125,6 +126,7 @@ struct UdDynPlan {
   int nstages;
   int radix[UD_FFT_MAX_STAGES];
   __device__ __forceinline__ int n() const { return n_; }
+  __device__ __forceinline__ int line_len() const { return n_; }
   __device__ __forceinline__ float2* run(float2* a, float2* b, const float2* tw, int L, int LS) const {
     int Ns = 1;
     for (int s = 0; s < nstages; ++s) {
@@ -213,12 +215,14 @@ struct UdIpStages<N, NS, L, THREADS, R0, Rest...> {
   }
 };
 
-// Plan concept used by the kernels:  kInPlace, n(), run(a, b, tw, L, LS) -> buffer holding the result.
+// Plan concept used by the kernels:  kInPlace, n(), line_len() (>= n: the points a line buffer and the staged twiddle
+// table must hold -- Bluestein plans work at a longer length), run(a, b, tw, L, LS) -> buffer holding the result.
 template <int N, int L, int THREADS, int... Rs>
 struct UdStaticPlanIP {
   static constexpr bool kInPlace = true;
   static constexpr int kN = N;
   __device__ __forceinline__ int n() const { return N; }
+  __device__ __forceinline__ int line_len() const { return N; }
   __device__ __forceinline__ float2* run(float2* a, float2*, const float2* tw, int, int) const {
     UdIpStages<N, 1, L, THREADS, Rs...>::run(a, tw);
     return a;

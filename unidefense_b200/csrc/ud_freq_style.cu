@@ -11,6 +11,7 @@
 //          two output rows per complex line, inverse row FFT, 1/(H*W) scaling, coalesced stores.
 #include "../../include/unidefense_b200.h"
 #include "ud_fft.cuh"
+#include "ud_fft_any.cuh"
 
 #define FS_ROW_T 256
 #define FS_ROW_L 12
@@ -26,9 +27,10 @@ fs_rows_fwd_kernel(Plan plan, const float* __restrict__ a, const float* __restri
                    float2* __restrict__ Yb, const float2* __restrict__ tw_g, int plane0, int H, int W) {
   extern __shared__ float2 smem[];
   const int n = plan.n();
-  const int LS = n | 1;
+  const int m = plan.line_len();     // == n except for Bluestein plans
+  const int LS = m | 1;
   float2* tw = smem;
-  float2* buf0 = tw + n;
+  float2* buf0 = tw + m;
   float2* buf1 = Plan::kInPlace ? buf0 : buf0 + FS_ROW_L * LS;
   W = n;
   const int Wh = n / 2 + 1;
@@ -36,7 +38,7 @@ fs_rows_fwd_kernel(Plan plan, const float* __restrict__ a, const float* __restri
   const int pl = blockIdx.y;
   const long long plane = plane0 + pl;
   const int r0 = blockIdx.x * FS_ROW_L;
-  for (int t = threadIdx.x; t < n; t += FS_ROW_T) tw[t] = __ldg(tw_g + t);
+  for (int t = threadIdx.x; t < m; t += FS_ROW_T) tw[t] = __ldg(tw_g + t);
   const float* ap = a + plane * (long long)H * W;
   const float* bp = b + plane * (long long)H * W;
   for (int p = 0; p < FS_ROW_L; ++p) {
@@ -75,9 +77,10 @@ fs_cols_kernel(Plan16 plan16, Plan8 plan8, float2* __restrict__ Ya, const float2
                const float* __restrict__ lmda, const float2* __restrict__ tw_g, int plane0, int C, int H, int W) {
   extern __shared__ float2 smem[];
   const int n = plan16.n();
-  const int LS = n | 1;
+  const int m = plan16.line_len();     // == n except for Bluestein plans
+  const int LS = m | 1;
   float2* tw = smem;
-  float2* buf0 = tw + n;
+  float2* buf0 = tw + m;
   float2* buf1 = Plan16::kInPlace ? buf0 : buf0 + FS_COL_L * LS;
   H = n;
   const int Wh = W / 2 + 1;
@@ -87,7 +90,7 @@ fs_cols_kernel(Plan16 plan16, Plan8 plan8, float2* __restrict__ Ya, const float2
   const float lam = __ldg(lmda + plane / C);
   const int k0 = blockIdx.x * FS_COL_K;
   const int ncols = min(FS_COL_K, Wh - k0);
-  for (int t = threadIdx.x; t < n; t += FS_COL_T) tw[t] = __ldg(tw_g + t);
+  for (int t = threadIdx.x; t < m; t += FS_COL_T) tw[t] = __ldg(tw_g + t);
   float2* Yap = Ya + (long long)pl * H * WhP;
   const float2* Ybp = Yb + (long long)pl * H * WhP;
   for (int t = threadIdx.x; t < H * FS_COL_L; t += FS_COL_T) {
@@ -136,9 +139,10 @@ fs_rows_inv_kernel(Plan plan, const float2* __restrict__ T, float* __restrict__ 
                    int plane0, int H, int W, float scale) {
   extern __shared__ float2 smem[];
   const int n = plan.n();
-  const int LS = n | 1;
+  const int m = plan.line_len();     // == n except for Bluestein plans
+  const int LS = m | 1;
   float2* tw = smem;
-  float2* buf0 = tw + n;
+  float2* buf0 = tw + m;
   float2* buf1 = Plan::kInPlace ? buf0 : buf0 + FS_ROW_L * LS;
   W = n;
   const int Wh = n / 2 + 1;
@@ -146,7 +150,7 @@ fs_rows_inv_kernel(Plan plan, const float2* __restrict__ T, float* __restrict__ 
   const int pl = blockIdx.y;
   const long long plane = plane0 + pl;
   const int r0 = blockIdx.x * (2 * FS_ROW_L);
-  for (int t = threadIdx.x; t < n; t += FS_ROW_T) tw[t] = __ldg(tw_g + t);
+  for (int t = threadIdx.x; t < m; t += FS_ROW_T) tw[t] = __ldg(tw_g + t);
   const float2* Tp = T + (long long)pl * H * WhP;
   // X_full[k] = T[k] (k < Wh, imaginary parts of self-paired bins dropped), X_full[n-k] = conj T[k];
   // V = Xa + i Xb, stored swapped for the inverse transform.
@@ -180,7 +184,14 @@ fs_rows_inv_kernel(Plan plan, const float2* __restrict__ T, float* __restrict__ 
 }
 
 static bool fs_static(int n) { return n == 380 || n == 256 || n == 224 || n == 299; }
-static size_t fs_smem(int n, int L) { return sizeof(float2) * ((size_t)n + (fs_static(n) ? 1 : 2) * (size_t)L * (n | 1)); }
+static int fs_line_len(int n) {
+  if (fs_static(n)) return n;
+  UdAnyPlan p;
+  return ud_make_any_plan(n, &p) ? p.m : 0;
+}
+static size_t fs_smem(int n, int m, int L) {
+  return sizeof(float2) * ((size_t)m + (fs_static(n) ? 1 : 2) * (size_t)L * (m | 1));
+}
 
 template <class K>
 static int fs_set_smem(K kernel, size_t bytes) {
@@ -202,7 +213,7 @@ static int fs_set_smem(K kernel, size_t bytes) {
     else if ((n) == 256) { UdStaticPlanIP<256, L, THREADS, 4, 4, 4, 4> P; __VA_ARGS__; }       \
     else if ((n) == 224) { UdStaticPlanIP<224, L, THREADS, 7, 4, 4, 2> P; __VA_ARGS__; }       \
     else if ((n) == 299) { UdStaticPlanIP<299, L, THREADS, 23, 13> P; __VA_ARGS__; }           \
-    else { UdDynPlan P; ud_make_dyn_plan((n), &P); __VA_ARGS__; }                              \
+    else { UdAnyPlan P; if (!ud_make_any_plan((n), &P)) return UD_ERR_UNSUPPORTED; __VA_ARGS__; } \
   } while (0)
 #define FS_PLAN2(n, P16, P8, ...)                                                                                          \
   do {                                                                                                                     \
@@ -210,7 +221,7 @@ static int fs_set_smem(K kernel, size_t bytes) {
     else if ((n) == 256) { UdStaticPlanIP<256, FS_COL_L, FS_COL_T, 4, 4, 4, 4> P16; UdStaticPlanIP<256, FS_COL_K, FS_COL_T, 4, 4, 4, 4> P8; __VA_ARGS__; } \
     else if ((n) == 224) { UdStaticPlanIP<224, FS_COL_L, FS_COL_T, 7, 4, 4, 2> P16; UdStaticPlanIP<224, FS_COL_K, FS_COL_T, 7, 4, 4, 2> P8; __VA_ARGS__; } \
     else if ((n) == 299) { UdStaticPlanIP<299, FS_COL_L, FS_COL_T, 23, 13> P16; UdStaticPlanIP<299, FS_COL_K, FS_COL_T, 23, 13> P8; __VA_ARGS__; } \
-    else { UdDynPlan P16; ud_make_dyn_plan((n), &P16); UdDynPlan P8 = P16; __VA_ARGS__; }                                  \
+    else { UdAnyPlan P16; if (!ud_make_any_plan((n), &P16)) return UD_ERR_UNSUPPORTED; UdAnyPlan P8 = P16; __VA_ARGS__; }  \
   } while (0)
 
 static int fs_chunk(int N, int C, int H, int W) {
@@ -229,8 +240,8 @@ extern "C" size_t ud_freq_style_workspace_bytes(int N, int C, int H, int W) {
 extern "C" int ud_freq_style_transfer(const float* content, const float* style, const float* lmda, float* out, void* ws,
                                       size_t ws_bytes, int N, int C, int H, int W, cudaStream_t stream) {
   UD_REQUIRE(N >= 0 && C >= 1 && H >= 1 && W >= 1, UD_ERR_INVALID, "freq_style: bad shape N=%d C=%d H=%d W=%d", N, C, H, W);
-  UD_REQUIRE(ud_fft_size_supported(H) && ud_fft_size_supported(W), UD_ERR_UNSUPPORTED,
-             "freq_style: FFT size %dx%d unsupported (prime factors must be <= 23, n <= %d)", H, W, UD_FFT_MAX_N);
+  UD_REQUIRE(H <= UD_FFT_MAX_N && W <= UD_FFT_MAX_N, UD_ERR_UNSUPPORTED, "freq_style: FFT size %dx%d unsupported (n <= %d)",
+             H, W, UD_FFT_MAX_N);
   if (N == 0) return UD_OK;
   UD_REQUIRE(content && style && lmda && out && ws, UD_ERR_INVALID, "freq_style: null pointer");
   UD_REQUIRE(ws_bytes >= ud_freq_style_workspace_bytes(N, C, H, W), UD_ERR_WORKSPACE, "freq_style: workspace too small");
@@ -238,10 +249,12 @@ extern "C" int ud_freq_style_transfer(const float* content, const float* style, 
   const int Wh = W / 2 + 1;
   float2* Ya = reinterpret_cast<float2*>(ws);
   float2* Yb = Ya + (size_t)chunk * C * H * fs_whp(W);
-  const float2* twW = ud_twiddles(W);
-  const float2* twH = ud_twiddles(H);
+  const int mW = fs_line_len(W), mH = fs_line_len(H);
+  if (!mW || !mH) return UD_ERR_UNSUPPORTED;
+  const float2* twW = ud_twiddles(mW);
+  const float2* twH = ud_twiddles(mH);
   if (!twW || !twH) return UD_ERR_CUDA;
-  const size_t smR = fs_smem(W, FS_ROW_L), smC = fs_smem(H, FS_COL_L);
+  const size_t smR = fs_smem(W, mW, FS_ROW_L), smC = fs_smem(H, mH, FS_COL_L);
   const float scale = 1.f / ((float)H * (float)W);
   int rc;
   for (int s0 = 0; s0 < N; s0 += chunk) {

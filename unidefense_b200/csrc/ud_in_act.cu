@@ -31,7 +31,7 @@ namespace cg = cooperative_groups;
 #define IA_MAX_CS 8
 
 template <int ACT>
-__device__ __forceinline__ float ia_sigmoid(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+__device__ __forceinline__ float ia_sigmoid(float z) { return ud_sigmoid_fast(z); }
 template <int ACT>
 __device__ __forceinline__ float ia_act(float z) {
   if (ACT == UD_ACT_RELU) return fmaxf(z, 0.f);
@@ -54,11 +54,11 @@ __device__ __forceinline__ float ia_act_grad(float z) {
 struct IaStat {
   float n, mean, m2;
 };
+// Branch-free: counts are 0 or >= 4, so max(n, 1) only changes the empty-with-empty case (f = 0, result = a).
 __device__ __forceinline__ IaStat ia_merge(IaStat a, IaStat b) {
   const float n = a.n + b.n;
-  if (n == 0.f) return a;
   const float d = b.mean - a.mean;
-  const float f = __fdividef(b.n, n);
+  const float f = b.n * ud_rcp_ftz(fmaxf(n, 1.f));
   IaStat r;
   r.n = n;
   r.mean = fmaf(d, f, a.mean);
@@ -72,8 +72,13 @@ __device__ __forceinline__ IaStat ia_warp_merge(IaStat s) {
     t.n = __shfl_xor_sync(0xffffffffu, s.n, o);
     t.mean = __shfl_xor_sync(0xffffffffu, s.mean, o);
     t.m2 = __shfl_xor_sync(0xffffffffu, s.m2, o);
-    // order the pair by lane so that both partners compute bit-identical results
-    s = ((threadIdx.x & o) == 0) ? ia_merge(s, t) : ia_merge(t, s);
+    // order the pair by lane so that both partners compute bit-identical results (one merge, operands selected)
+    const bool lo = (threadIdx.x & o) == 0;
+    IaStat a, b;
+    a.n = lo ? s.n : t.n;          b.n = lo ? t.n : s.n;
+    a.mean = lo ? s.mean : t.mean; b.mean = lo ? t.mean : s.mean;
+    a.m2 = lo ? s.m2 : t.m2;       b.m2 = lo ? t.m2 : s.m2;
+    s = ia_merge(a, b);
   }
   return s;
 }
@@ -148,45 +153,47 @@ __device__ __forceinline__ float ia_fold_sum(const float (*slots)[K], int k, int
   return ud_warp_sum(v);
 }
 
-template <bool CLUSTER, int ACT, bool WANT_MEAN>
-__global__ void __launch_bounds__(IA_THREADS, 4)
-ia_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-              float4* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-              float* __restrict__ ymean_out, int planes, int C, int E4, int G, int cs, int vpt, float eps) {
-  __shared__ float slots[IA_MAX_CS * IA_WARPS][3];
-  __shared__ float yslots[IA_MAX_CS * IA_WARPS][1];
-  const IaGeom ge = ia_geom<CLUSTER>(planes, G, cs);
-  const int lane = threadIdx.x & 31;
-  const int per_w = (E4 + ge.nw - 1) / ge.nw;
-  const int beg = ge.wsub * per_w;
-  const int end = ge.live ? min(E4, beg + per_w) : 0;
-  const float4* xp = x + (long long)ge.plane * E4;
-  float4 v[IA_VMAX_FWD];
-  float s = 0.f;
-  int cnt = 0;
+// Slot validity of a lane.  A warp's slab of `len` float4 is read lane-strided: slot i of lane l is element
+// i*32 + l.  FAST (warp-uniform: the slab fills all but possibly the last of the VPT slots -- every shape of the
+// shipped configurations) makes slots 0..VPT-2 unconditional at compile time and leaves ONE runtime predicate for the
+// last slot, so the unrolled body carries no per-slot compare/branch/address arithmetic (which, with the range-checked
+// special functions, was 2/3 of the instructions of these issue-bound kernels).
+template <bool FAST, int VPT>
+__device__ __forceinline__ bool ia_ok(int i, int lane, int len, bool last_ok) {
+  if (FAST) return (i < VPT - 1) ? true : last_ok;
+  return i * 32 + lane < len;
+}
+
+template <bool CLUSTER, int ACT, bool WANT_MEAN, int VPT, bool FAST>
+__device__ __forceinline__ void ia_fwd_body(const float4* __restrict__ xl, float4* __restrict__ yl, int lane, int len,
+                                            float (*slots)[3], float (*yslots)[1], const IaGeom& ge, int cs, float g,
+                                            float b, float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                            float* __restrict__ ymean_out) {
+  const bool last_ok = (VPT - 1) * 32 + lane < len;
+  float4 v[VPT];
+  int nv = 0;
 #pragma unroll
-  for (int i = 0; i < IA_VMAX_FWD; ++i) {
-    const int idx = beg + i * 32 + lane;
-    if (i < vpt && idx < end) {
-      v[i] = __ldcs(xp + idx);
-      cnt += 4;
+  for (int i = 0; i < VPT; ++i) {
+    if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
+      v[i] = __ldcs(xl + i * 32);
+      ++nv;
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < IA_VMAX_FWD; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int i = 0; i < VPT; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   // thread-local two-pass statistics, then one merge tree
   IaStat st;
-  st.n = (float)cnt;
-  st.mean = cnt ? s / (float)cnt : 0.f;
+  st.n = 4.f * (float)nv;
+  st.mean = nv ? s * __frcp_rn(st.n) : 0.f;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < IA_VMAX_FWD; ++i) {
-    const int idx = beg + i * 32 + lane;
-    if (i < vpt && idx < end) {
-      const float a = v[i].x - st.mean, b = v[i].y - st.mean, c = v[i].z - st.mean, d = v[i].w - st.mean;
-      q += (a * a + b * b) + (c * c + d * d);
+  for (int i = 0; i < VPT; ++i) {
+    if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
+      const float a = v[i].x - st.mean, bq = v[i].y - st.mean, c = v[i].z - st.mean, d = v[i].w - st.mean;
+      q += (a * a + bq * bq) + (c * c + d * d);
     }
   }
   st.m2 = q;
@@ -196,23 +203,18 @@ ia_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ gamma, con
   const IaStat tot = ia_fold_stats(slots, ge.slot0, ge.nw);
   const float mu = tot.mean;
   const float rstd = rsqrtf(tot.m2 / fmaxf(tot.n, 1.f) + eps);
-  const int ch = ge.live ? ge.plane % C : 0;
-  const float g = gamma ? __ldg(gamma + ch) : 1.f;
-  const float b = beta ? __ldg(beta + ch) : 0.f;
   const float a_ = g * rstd, b_ = b - mu * g * rstd;
-  float4* yp = y + (long long)ge.plane * E4;
   float ys = 0.f;
 #pragma unroll
-  for (int i = 0; i < IA_VMAX_FWD; ++i) {
-    const int idx = beg + i * 32 + lane;
-    if (i < vpt && idx < end) {
+  for (int i = 0; i < VPT; ++i) {
+    if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
       float4 o;
       o.x = ia_act<ACT>(fmaf(v[i].x, a_, b_));
       o.y = ia_act<ACT>(fmaf(v[i].y, a_, b_));
       o.z = ia_act<ACT>(fmaf(v[i].z, a_, b_));
       o.w = ia_act<ACT>(fmaf(v[i].w, a_, b_));
       if (WANT_MEAN) ys += (o.x + o.y) + (o.z + o.w);
-      yp[idx] = o;
+      yl[i * 32] = o;
     }
   }
   const bool writer = ge.live && ge.wsub == 0 && lane == 0;
@@ -229,33 +231,45 @@ ia_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ gamma, con
   }
 }
 
-template <bool CLUSTER, int ACT>
+template <bool CLUSTER, int ACT, bool WANT_MEAN, int VPT>
 __global__ void __launch_bounds__(IA_THREADS, 4)
-ia_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const float* __restrict__ gamma,
-              const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd_in,
-              const float* __restrict__ g_ymean, float4* __restrict__ gx, float* __restrict__ s1_out,
-              float* __restrict__ s2_out, int planes, int C, int E4, int G, int cs, int vpt) {
-  __shared__ __align__(8) float slots[IA_MAX_CS * IA_WARPS][2];
+ia_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float4* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+              float* __restrict__ ymean_out, int planes, int C, int E4, int G, int cs, float eps) {
+  __shared__ float slots[IA_MAX_CS * IA_WARPS][3];
+  __shared__ float yslots[IA_MAX_CS * IA_WARPS][1];
   const IaGeom ge = ia_geom<CLUSTER>(planes, G, cs);
   const int lane = threadIdx.x & 31;
   const int per_w = (E4 + ge.nw - 1) / ge.nw;
   const int beg = ge.wsub * per_w;
-  const int end = ge.live ? min(E4, beg + per_w) : 0;
+  const int len = ge.live ? max(min(E4, beg + per_w) - beg, 0) : 0;     // float4 of this warp's slab (<= VPT*32)
   const int pl = ge.live ? ge.plane : 0;
-  const long long base = (long long)pl * E4;
+  const float4* xl = x + (long long)pl * E4 + beg + lane;
+  float4* yl = y + (long long)pl * E4 + beg + lane;
   const int ch = pl % C;
   const float g = gamma ? __ldg(gamma + ch) : 1.f;
   const float b = beta ? __ldg(beta + ch) : 0.f;
-  const float mu = mean[pl], rstd = rstd_in[pl];
-  const float invE = 1.f / (4.f * (float)E4);
-  const float gadd = g_ymean ? g_ymean[pl] * invE : 0.f;  // d mean(y) term
-  float4 xh[IA_VMAX_BWD], gz[IA_VMAX_BWD];
+  // both branches run the same barriers / cluster syncs, so a CTA (cluster) may mix them
+  if (len > (VPT - 1) * 32)
+    ia_fwd_body<CLUSTER, ACT, WANT_MEAN, VPT, true>(xl, yl, lane, len, slots, yslots, ge, cs, g, b, eps, mean_out, rstd_out,
+                                                    ymean_out);
+  else
+    ia_fwd_body<CLUSTER, ACT, WANT_MEAN, VPT, false>(xl, yl, lane, len, slots, yslots, ge, cs, g, b, eps, mean_out, rstd_out,
+                                                     ymean_out);
+}
+
+template <bool CLUSTER, int ACT, int VPT, bool FAST>
+__device__ __forceinline__ void ia_bwd_body(const float4* __restrict__ xl, const float4* __restrict__ gl,
+                                            float4* __restrict__ ol, int lane, int len, float (*slots)[2],
+                                            const IaGeom& ge, int cs, float g, float b, float mu, float rstd, float gadd,
+                                            float invE, float* __restrict__ s1_out, float* __restrict__ s2_out) {
+  const bool last_ok = (VPT - 1) * 32 + lane < len;
+  float4 xh[VPT], gz[VPT];
 #pragma unroll
-  for (int i = 0; i < IA_VMAX_BWD; ++i) {   // all loads in flight before any math
-    const int idx = beg + i * 32 + lane;
-    if (i < vpt && idx < end) {
-      xh[i] = __ldcs(x + base + idx);
-      gz[i] = __ldcs(gy + base + idx);
+  for (int i = 0; i < VPT; ++i) {   // all loads in flight before any math
+    if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
+      xh[i] = __ldcs(xl + i * 32);
+      gz[i] = __ldcs(gl + i * 32);
     } else {
       xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -264,9 +278,8 @@ ia_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const
   float s1 = 0.f, s2 = 0.f;
   const float nmr = -mu * rstd;
 #pragma unroll
-  for (int i = 0; i < IA_VMAX_BWD; ++i) {
-    const int idx = beg + i * 32 + lane;
-    if (i < vpt && idx < end) {
+  for (int i = 0; i < VPT; ++i) {
+    if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
       float4 h, z;
       h.x = fmaf(xh[i].x, rstd, nmr); h.y = fmaf(xh[i].y, rstd, nmr);
       h.z = fmaf(xh[i].z, rstd, nmr); h.w = fmaf(xh[i].w, rstd, nmr);
@@ -293,21 +306,48 @@ ia_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const
   }
   const float m1 = S1 * invE, m2 = S2 * invE, k = g * rstd;
 #pragma unroll
-  for (int i = 0; i < IA_VMAX_BWD; ++i) {
-    const int idx = beg + i * 32 + lane;
-    if (i < vpt && idx < end) {
+  for (int i = 0; i < VPT; ++i) {
+    if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
       float4 o;
       o.x = k * (gz[i].x - m1 - xh[i].x * m2);
       o.y = k * (gz[i].y - m1 - xh[i].y * m2);
       o.z = k * (gz[i].z - m1 - xh[i].z * m2);
       o.w = k * (gz[i].w - m1 - xh[i].w * m2);
-      gx[base + idx] = o;
+      ol[i * 32] = o;
     }
   }
   if (ge.live && ge.wsub == 0 && lane == 0) {
     s1_out[ge.plane] = S1;
     s2_out[ge.plane] = S2;
   }
+}
+
+template <bool CLUSTER, int ACT, int VPT>
+__global__ void __launch_bounds__(IA_THREADS, 4)
+ia_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const float* __restrict__ gamma,
+              const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd_in,
+              const float* __restrict__ g_ymean, float4* __restrict__ gx, float* __restrict__ s1_out,
+              float* __restrict__ s2_out, int planes, int C, int E4, int G, int cs) {
+  __shared__ __align__(8) float slots[IA_MAX_CS * IA_WARPS][2];
+  const IaGeom ge = ia_geom<CLUSTER>(planes, G, cs);
+  const int lane = threadIdx.x & 31;
+  const int per_w = (E4 + ge.nw - 1) / ge.nw;
+  const int beg = ge.wsub * per_w;
+  const int len = ge.live ? max(min(E4, beg + per_w) - beg, 0) : 0;
+  const int pl = ge.live ? ge.plane : 0;
+  const long long off = (long long)pl * E4 + beg + lane;
+  const int ch = pl % C;
+  const float g = gamma ? __ldg(gamma + ch) : 1.f;
+  const float b = beta ? __ldg(beta + ch) : 0.f;
+  const float mu = mean[pl], rstd = rstd_in[pl];
+  const float invE = 1.f / (4.f * (float)E4);
+  const float gadd = g_ymean ? g_ymean[pl] * invE : 0.f;  // d mean(y) term
+  if (len > (VPT - 1) * 32)
+    ia_bwd_body<CLUSTER, ACT, VPT, true>(x + off, gy + off, gx + off, lane, len, slots, ge, cs, g, b, mu, rstd, gadd, invE,
+                                         s1_out, s2_out);
+  else
+    ia_bwd_body<CLUSTER, ACT, VPT, false>(x + off, gy + off, gx + off, lane, len, slots, ge, cs, g, b, mu, rstd, gadd,
+                                          invE, s1_out, s2_out);
 }
 
 // ---- generic fallback: any plane size (odd E, huge planes): one CTA per plane, re-reads hit L1/L2 ----
@@ -456,14 +496,20 @@ extern "C" int ud_in_act_fwd(const float* x, const float* gamma, const float* be
   if (aligned && ia_pick(HW, IA_VMAX_FWD, &G, &cs, &vpt)) {
     const float4* x4 = reinterpret_cast<const float4*>(x);
     float4* y4 = reinterpret_cast<float4*>(y);
-#define IA_FWD(CL, WM, BLOCKS)                                                                                      \
-  IA_ACT_SWITCH(act, return ia_launch(ia_fwd_kernel<CL, ACT_, WM>, BLOCKS, cs, stream, x4, gamma, beta, y4, mean, rstd, \
-                                      ymean, planes, C, HW / 4, G, cs, vpt, eps))
+#define IA_FWD_V(CL, WM, BLOCKS, V)                                                                                  \
+  IA_ACT_SWITCH(act, return ia_launch(ia_fwd_kernel<CL, ACT_, WM, V>, BLOCKS, cs, stream, x4, gamma, beta, y4, mean, rstd, \
+                                      ymean, planes, C, HW / 4, G, cs, eps))
+#define IA_FWD(CL, WM, BLOCKS)                       \
+  do {                                               \
+    if (vpt <= 5) IA_FWD_V(CL, WM, BLOCKS, 5);       \
+    IA_FWD_V(CL, WM, BLOCKS, IA_VMAX_FWD);           \
+  } while (0)
     if (cs == 1 && ymean) IA_FWD(false, true, ud_cdiv(planes, IA_WARPS / G));
     if (cs == 1) IA_FWD(false, false, ud_cdiv(planes, IA_WARPS / G));
     if (ymean) IA_FWD(true, true, planes * cs);
     IA_FWD(true, false, planes * cs);
 #undef IA_FWD
+#undef IA_FWD_V
   }
   ia_fwd_generic_kernel<<<planes, IA_THREADS, 0, stream>>>(x, gamma, beta, y, mean, rstd, ymean, C, HW, eps, act);
   return ud_check_launch("ia_fwd_generic");
@@ -497,11 +543,11 @@ extern "C" int ud_in_act_bwd(const float* x, const float* gy, const float* gamma
     float4* o4 = reinterpret_cast<float4*>(gx);
     rc = UD_OK;
     if (cs == 1)
-      IA_ACT_SWITCH(act, rc = ia_launch(ia_bwd_kernel<false, ACT_>, ud_cdiv(planes, IA_WARPS / G), 1, stream, x4, g4, gamma,
-                                        beta, mean, rstd, g_ymean, o4, s1, s2, planes, C, HW / 4, G, cs, vpt));
+      IA_ACT_SWITCH(act, rc = ia_launch(ia_bwd_kernel<false, ACT_, IA_VMAX_BWD>, ud_cdiv(planes, IA_WARPS / G), 1, stream, x4,
+                                        g4, gamma, beta, mean, rstd, g_ymean, o4, s1, s2, planes, C, HW / 4, G, cs));
     else
-      IA_ACT_SWITCH(act, rc = ia_launch(ia_bwd_kernel<true, ACT_>, planes * cs, cs, stream, x4, g4, gamma, beta, mean,
-                                        rstd, g_ymean, o4, s1, s2, planes, C, HW / 4, G, cs, vpt));
+      IA_ACT_SWITCH(act, rc = ia_launch(ia_bwd_kernel<true, ACT_, IA_VMAX_BWD>, planes * cs, cs, stream, x4, g4, gamma, beta,
+                                        mean, rstd, g_ymean, o4, s1, s2, planes, C, HW / 4, G, cs));
     if (rc != UD_OK) return rc;
   } else {
     ia_bwd_generic_kernel<<<planes, IA_THREADS, 0, stream>>>(x, gy, gamma, beta, mean, rstd, g_ymean, gx, s1, s2, C,

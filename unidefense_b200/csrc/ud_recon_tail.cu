@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "ud_fft.cuh"
+#include "ud_fft_any.cuh"
 
 // second-generation kernels for the configured image sizes (ud_recon_tail2.cu)
 bool ud_rt2_supported(int h, int w, int H, int W);
@@ -84,9 +85,10 @@ rt_rows_fwd_kernel(Plan plan, const float* __restrict__ dec, const float* __rest
                    const float2* __restrict__ xtab_g, int plane0, int h, int w, int H, int W, int row_tiles) {
   extern __shared__ float2 smem[];
   const int n = plan.n();  // == W
-  const int LS = n | 1;
+  const int m = plan.line_len();     // == n except for Bluestein plans
+  const int LS = m | 1;
   float2* tw = smem;
-  float2* xtab = tw + n;
+  float2* xtab = tw + m;
   float2* buf0 = xtab + n;
   float2* buf1 = Plan::kInPlace ? buf0 : buf0 + RT_ROW_L * LS;
   float* vbuf = reinterpret_cast<float*>(buf1 + RT_ROW_L * LS);
@@ -100,10 +102,8 @@ rt_rows_fwd_kernel(Plan plan, const float* __restrict__ dec, const float* __rest
   const int Wh = n / 2 + 1;
   const int WhP = (Wh + 15) & ~15;
 
-  for (int t = threadIdx.x; t < n; t += RT_ROW_T) {
-    tw[t] = __ldg(tw_g + t);
-    xtab[t] = __ldg(xtab_g + t);
-  }
+  for (int t = threadIdx.x; t < m; t += RT_ROW_T) tw[t] = __ldg(tw_g + t);
+  for (int t = threadIdx.x; t < n; t += RT_ROW_T) xtab[t] = __ldg(xtab_g + t);
   const float* decp = dec + plane * (long long)h * w;
   const float* xp = x + plane * (long long)H * W;
   float* recp = rec + plane * (long long)H * W;
@@ -192,9 +192,10 @@ rt_cols_fwd_kernel(Plan plan, const float2* __restrict__ Y, float* __restrict__ 
                    int col_tiles) {
   extern __shared__ float2 smem[];
   const int n = plan.n();  // == H
-  const int LS = n | 1;
+  const int m = plan.line_len();     // == n except for Bluestein plans
+  const int LS = m | 1;
   float2* tw = smem;
-  float2* buf0 = tw + n;
+  float2* buf0 = tw + m;
   float2* buf1 = Plan::kInPlace ? buf0 : buf0 + RT_COL_L * LS;
   __shared__ float red[33];
 
@@ -207,7 +208,7 @@ rt_cols_fwd_kernel(Plan plan, const float2* __restrict__ Y, float* __restrict__ 
   const int k0 = tile * RT_COL_L;
   const int ncols = min(RT_COL_L, Wh - k0);
 
-  for (int t = threadIdx.x; t < n; t += RT_COL_T) tw[t] = __ldg(tw_g + t);
+  for (int t = threadIdx.x; t < m; t += RT_COL_T) tw[t] = __ldg(tw_g + t);
   const float2* Yp = Y + (long long)pl * H * WhP;
   for (int t = threadIdx.x; t < H * RT_COL_L; t += RT_COL_T) {
     const int r = t / RT_COL_L, cc = t - r * RT_COL_L;
@@ -264,9 +265,10 @@ rt_cols_bwd_kernel(Plan plan, const uint8_t* __restrict__ signs, const float* __
                    float gscale) {
   extern __shared__ float2 smem[];
   const int n = plan.n();
-  const int LS = n | 1;
+  const int m = plan.line_len();     // == n except for Bluestein plans
+  const int LS = m | 1;
   float2* tw = smem;
-  float2* buf0 = tw + n;
+  float2* buf0 = tw + m;
   float2* buf1 = Plan::kInPlace ? buf0 : buf0 + RT_COL_L * LS;
 
   const int tile = blockIdx.x;
@@ -281,7 +283,7 @@ rt_cols_bwd_kernel(Plan plan, const uint8_t* __restrict__ signs, const float* __
   const int k0 = tile * RT_COL_L;
   const int ncols = min(RT_COL_L, Wh - k0);
 
-  for (int t = threadIdx.x; t < n; t += RT_COL_T) tw[t] = __ldg(tw_g + t);
+  for (int t = threadIdx.x; t < m; t += RT_COL_T) tw[t] = __ldg(tw_g + t);
   for (int t = threadIdx.x; t < RT_COL_L * H; t += RT_COL_T) {
     const int cc = t / H, j = t - cc * H;
     float2 v = make_float2(0.f, 0.f);
@@ -326,9 +328,10 @@ rt_rows_bwd_kernel(Plan plan, const float* __restrict__ dec, const float* __rest
                    int w, int H, int W, float sp_scale) {
   extern __shared__ float2 smem[];
   const int n = plan.n();  // == W
-  const int LS = n | 1;
+  const int m = plan.line_len();     // == n except for Bluestein plans
+  const int LS = m | 1;
   float2* tw = smem;
-  float2* xtab = tw + n;
+  float2* xtab = tw + m;
   float2* buf0 = xtab + n;
   float2* buf1 = Plan::kInPlace ? buf0 : buf0 + RT_ROW_L * LS;
   float* vbuf = reinterpret_cast<float*>(buf1 + RT_ROW_L * LS);
@@ -346,10 +349,8 @@ rt_rows_bwd_kernel(Plan plan, const float* __restrict__ dec, const float* __rest
   const int WhP = (Wh + 15) & ~15;
   const int nrows = min(2 * RT_ROW_L, H - r0);
 
-  for (int t = threadIdx.x; t < n; t += RT_ROW_T) {
-    tw[t] = __ldg(tw_g + t);
-    xtab[t] = __ldg(xtab_g + t);
-  }
+  for (int t = threadIdx.x; t < m; t += RT_ROW_T) tw[t] = __ldg(tw_g + t);
+  for (int t = threadIdx.x; t < n; t += RT_ROW_T) xtab[t] = __ldg(xtab_g + t);
   // sign(rec - x) of the tile first (2+2 bits per row pair and column), while the buffer is still free:
   // x is prefetched into the lines with cp.async exactly like the forward does.
   uint8_t* sgn = reinterpret_cast<uint8_t*>(vbuf + 4 * RT_VGRP * w);   // [RT_ROW_L][n]
@@ -539,14 +540,20 @@ rt_rows_bwd_kernel(Plan plan, const float* __restrict__ dec, const float* __rest
 // host side
 // ------------------------------------------------------------------------------------------
 static bool rt_static_size(int n) { return n == 380 || n == 256 || n == 224 || n == 299; }
-static size_t rt_rows_smem(int n, int w) {
+// points per line buffer / staged twiddles: n, or the Bluestein length for sizes with a prime factor > 23 (0 = error)
+static int rt_line_len(int n) {
+  if (rt_static_size(n)) return n;
+  UdAnyPlan p;
+  return ud_make_any_plan(n, &p) ? p.m : 0;
+}
+static size_t rt_rows_smem(int n, int m, int w) {
   const size_t bufs = rt_static_size(n) ? 1 : 2;
-  return sizeof(float2) * (2ull * n + bufs * RT_ROW_L * (size_t)(n | 1)) + sizeof(float) * 4ull * RT_VGRP * w +
+  return sizeof(float2) * ((size_t)m + n + bufs * RT_ROW_L * (size_t)(m | 1)) + sizeof(float) * 4ull * RT_VGRP * w +
          (size_t)RT_ROW_L * n;   // + sign bytes of the tile (rows_bwd)
 }
-static size_t rt_cols_smem(int n) {
+static size_t rt_cols_smem(int n, int m) {
   const size_t bufs = rt_static_size(n) ? 1 : 2;
-  return sizeof(float2) * ((size_t)n + bufs * RT_COL_L * (size_t)(n | 1));
+  return sizeof(float2) * ((size_t)m + bufs * RT_COL_L * (size_t)(m | 1));
 }
 
 static size_t rt_plane_bytes(int H, int W) {
@@ -577,14 +584,15 @@ extern "C" size_t ud_recon_tail_signs_bytes(int N, int C, int H, int W) {
   return (size_t)N * C * (W / 2 + 1) * H;
 }
 
-// Runs the body with PLANVAR bound to the in-place static plan for n when one exists, else a dynamic plan.
+// Runs the body with PLANVAR bound to the in-place static plan for n when one exists, else a run-time plan (mixed radix,
+// or Bluestein for sizes with a prime factor > 23).
 #define RT_DISPATCH_PLAN(n, L, THREADS, PLANVAR, ...)                                                    \
   do {                                                                                                   \
     if ((n) == 380) { UdStaticPlanIP<380, L, THREADS, 19, 5, 4> PLANVAR; __VA_ARGS__; }                  \
     else if ((n) == 256) { UdStaticPlanIP<256, L, THREADS, 4, 4, 4, 4> PLANVAR; __VA_ARGS__; }           \
     else if ((n) == 224) { UdStaticPlanIP<224, L, THREADS, 7, 4, 4, 2> PLANVAR; __VA_ARGS__; }           \
     else if ((n) == 299) { UdStaticPlanIP<299, L, THREADS, 23, 13> PLANVAR; __VA_ARGS__; }               \
-    else { UdDynPlan PLANVAR; ud_make_dyn_plan((n), &PLANVAR); __VA_ARGS__; }                            \
+    else { UdAnyPlan PLANVAR; if (!ud_make_any_plan((n), &PLANVAR)) return UD_ERR_UNSUPPORTED; __VA_ARGS__; } \
   } while (0)
 
 template <class K>
@@ -604,8 +612,8 @@ static int rt_set_smem(K kernel, size_t bytes) {
 static int rt_validate(int N, int C, int h, int w, int H, int W) {
   UD_REQUIRE(N >= 0 && C >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1, UD_ERR_INVALID,
              "recon_tail: bad shape N=%d C=%d h=%d w=%d H=%d W=%d", N, C, h, w, H, W);
-  UD_REQUIRE(ud_fft_size_supported(H) && ud_fft_size_supported(W), UD_ERR_UNSUPPORTED,
-             "recon_tail: FFT size %dx%d unsupported (prime factors must be <= 23, n <= %d)", H, W, UD_FFT_MAX_N);
+  UD_REQUIRE(H <= UD_FFT_MAX_N && W <= UD_FFT_MAX_N, UD_ERR_UNSUPPORTED,
+             "recon_tail: FFT size %dx%d unsupported (n <= %d)", H, W, UD_FFT_MAX_N);
   UD_REQUIRE((long long)N * C <= 65535LL * 64, UD_ERR_UNSUPPORTED, "recon_tail: too many planes");
   return UD_OK;
 }
@@ -632,12 +640,14 @@ extern "C" int ud_recon_tail_fwd(const float* dec, const float* x, float* rec, f
   float* part_sp = reinterpret_cast<float*>(p);
   p += ud_align_up((size_t)N * C * row_tiles * sizeof(float), 256);
   float* part_fr = reinterpret_cast<float*>(p);
-  const float2* twW = ud_twiddles(W);
-  const float2* twH = ud_twiddles(H);
+  const int mW = rt_line_len(W), mH = rt_line_len(H);
+  if (!mW || !mH) return UD_ERR_UNSUPPORTED;
+  const float2* twW = ud_twiddles(mW);
+  const float2* twH = ud_twiddles(mH);
   const float2* ytab = ud_lerp_table(h, H);
   const float2* xtab = ud_lerp_table(w, W);
   if (!twW || !twH || !ytab || !xtab) return UD_ERR_CUDA;
-  const size_t smW = rt_rows_smem(W, w), smH = rt_cols_smem(H);
+  const size_t smW = rt_rows_smem(W, mW, w), smH = rt_cols_smem(H, mH);
 
   for (int s0 = 0; s0 < N; s0 += chunk) {
     const int ns = (N - s0 < chunk) ? (N - s0) : chunk;
@@ -684,14 +694,16 @@ extern "C" int ud_recon_tail_bwd(const float* dec, const float* x, const uint8_t
   const int row_tiles = v2 ? ud_cdiv((H + 1) / 2, RT2_PAIRS_PER_TILE) : ud_cdiv(H, 2 * RT_ROW_L);
   const int col_tiles = v2 ? ud_cdiv(Wh, RT2_COLS_PER_TILE) : ud_cdiv(Wh, RT_COL_L);
   float2* T = reinterpret_cast<float2*>(ws);
-  const float2* twW = ud_twiddles(W);
-  const float2* twH = ud_twiddles(H);
+  const int mW = rt_line_len(W), mH = rt_line_len(H);
+  if (!mW || !mH) return UD_ERR_UNSUPPORTED;
+  const float2* twW = ud_twiddles(mW);
+  const float2* twH = ud_twiddles(mH);
   const float2* ytab = ud_lerp_table(h, H);
   const float2* xtab = ud_lerp_table(w, W);
   if (!twW || !twH || !ytab || !xtab) return UD_ERR_CUDA;
   const int2* jtab = ud_lerp_ranges(w, W);
   if (!jtab) return UD_ERR_CUDA;
-  const size_t smH = rt_cols_smem(H), smW = rt_rows_smem(W, w);
+  const size_t smH = rt_cols_smem(H, mH), smW = rt_rows_smem(W, mW, w);
   // freq[n] = nrm/(C*H*Wh) * sum |D'| with D' the unnormalised spectrum, so the sign spectrum
   // carries nrm/(C*H*Wh) and the adjoint of the unnormalised forward is the unnormalised inverse.
   const float nrm = norm_ortho ? 1.f / sqrtf((float)H * (float)W) : 1.f;

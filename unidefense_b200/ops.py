@@ -200,15 +200,19 @@ def attn_prep(pred, x, size, norm="ortho"):
 def _rfft2_raw(x, norm_ortho, adjoint):
     N, C, h, w = x.shape
     xf = torch.empty(N, 2 * C, h, w // 2 + 1, device=x.device, dtype=torch.float32)
-    L.check(L.lib().ud_rfft2_cat(L.ptr(x), L.ptr(xf), N, C, h, w, norm_ortho, adjoint, L.stream()), "rfft2_cat")
+    nws = L.lib().ud_rfft2_workspace_bytes(N, C, h, w)          # 0 for the small-plane path (h, w <= 64)
+    ws = L.workspace(nws, x.device) if nws else None
+    L.check(L.lib().ud_rfft2(L.ptr(x), L.ptr(xf), L.ptr(ws), nws, N, C, h, w, norm_ortho, adjoint, L.stream()), "rfft2_cat")
     return xf
 
 
 def _irfft2_raw(xf, mask, h, w, norm_ortho, adjoint):
     N, C2 = xf.shape[:2]
     y = torch.empty(N, C2 // 2, h, w, device=xf.device, dtype=torch.float32)
-    L.check(L.lib().ud_irfft2_cat(L.ptr(xf), L.ptr(mask), L.ptr(y), N, C2 // 2, h, w, norm_ortho, adjoint, L.stream()),
-            "irfft2_cat")
+    nws = L.lib().ud_rfft2_workspace_bytes(N, C2 // 2, h, w)
+    ws = L.workspace(nws, xf.device) if nws else None
+    L.check(L.lib().ud_irfft2(L.ptr(xf), L.ptr(mask), L.ptr(y), L.ptr(ws), nws, N, C2 // 2, h, w, norm_ortho, adjoint,
+                              L.stream()), "irfft2_cat")
     return y
 
 
@@ -693,16 +697,25 @@ def freq_style_transfer(content, style, lmda):
 
 
 def spatial_style_transfer(content, style, lmda):
-    """SpatialStyleTransfer (model/modules.py:59-76): exact histogram matching; lmda [B].
-    Library composition (CUB segmented sort through torch.sort) -- SURVEY.md marks the sort optional."""
+    """SpatialStyleTransfer (model/modules.py:59-76): exact histogram (rank) matching per (n, c) plane; lmda [B].
+    One stable radix sort per plane with the blend fused into the last pass (csrc/ud_style_sort.cu) instead of the
+    reference's two torch.sort + argsort + gather."""
+    content, style = content.detach().contiguous(), style.detach().contiguous()
     L.require_cuda_f32(content, style)
+    if content.shape != style.shape or content.dim() != 4:
+        raise AssertionError(f"spatial_style_transfer: content {tuple(content.shape)} and style {tuple(style.shape)} "
+                             "must share one [B,C,H,W] shape")          # the reference asserts (modules.py:61)
     B, C, H, W = content.shape
-    lm = lmda.reshape(-1, 1, 1).to(content)
-    cf = content.reshape(B, C, -1)
-    _, idx = torch.sort(cf, dim=-1)
-    vs, _ = torch.sort(style.reshape(B, C, -1), dim=-1)
-    matched = torch.empty_like(cf).scatter_(-1, idx, vs)        # == vs.gather(-1, idx.argsort(-1))
-    return (cf + (1 - lm) * matched - (1 - lm) * cf).view(B, C, H, W)
+    lm = lmda.detach().reshape(-1).to(device=content.device, dtype=torch.float32).contiguous()
+    if lm.numel() != B:
+        raise ValueError(f"spatial_style_transfer: lmda has {lm.numel()} entries for a batch of {B}")
+    out = torch.empty_like(content)
+    lib = L.lib()
+    nws = lib.ud_spatial_style_workspace_bytes(B, C, H * W)
+    ws = L.workspace(nws, content.device)
+    L.check(lib.ud_spatial_style_transfer(L.ptr(content), L.ptr(style), L.ptr(lm), L.ptr(out), L.ptr(ws), nws, B, C, H * W,
+                                          L.stream()), "spatial_style")
+    return out
 
 
 def coral_batch(source, target):
