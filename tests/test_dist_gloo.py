@@ -99,3 +99,51 @@ def test_bench_reference_arm_only_rank0_prints():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _scalars_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from unidefense_b200 import parallel as PAR
+        g = torch.Generator().manual_seed(100 + rank)
+        ret = {"total_loss": torch.rand((), generator=g), "cls_loss": torch.rand(1, generator=g), "cls_out": torch.rand(4, 2),
+               "real_rec_loss": torch.rand((), generator=g) * 3, "fac_loss": 0.25 * (rank + 1)}
+        acc = torch.rand((), generator=g)
+        # the reference's way: one all-reduce + one .item() per logged key (engine/forgery_engine.py:279-287)
+        ref = {}
+        for k, v in ret.items():
+            if "loss" in k:
+                t = v if torch.is_tensor(v) else torch.tensor(v)
+                rt = t.clone()
+                dist.all_reduce(rt)
+                rt /= float(dist.get_world_size())
+                ref[k] = rt.reshape(-1)[0].item()
+        rt = acc.clone()
+        dist.all_reduce(rt)
+        ref["acc"] = (rt / float(world)).item()
+        packed = PAR.reduce_scalars({**PAR.logged_losses(ret), "acc": acc})
+        single = PAR.reduce_tensor(ret["total_loss"]).item()
+        out[rank] = dict(ref=ref, packed=packed, single=single)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_packed_logging_reduction_equals_per_key_reduce_tensor():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_scalars_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in (0, 1):
+        o = out[r]
+        assert list(o["packed"]) == ["total_loss", "cls_loss", "real_rec_loss", "fac_loss", "acc"]      # "cls_out" is not a loss
+        for k, v in o["ref"].items():
+            assert o["packed"][k] == pytest.approx(v, rel=1e-6, abs=1e-7), k
+        assert o["single"] == pytest.approx(o["ref"]["total_loss"], rel=1e-6)
+    assert out[0]["packed"] == out[1]["packed"]
+
+
+def test_packed_reduction_without_a_process_group():
+    from unidefense_b200 import parallel as PAR
+    got = PAR.reduce_scalars({"a_loss": torch.tensor(1.5), "b": 2.0})
+    assert got == {"a_loss": 1.5, "b": 2.0} and PAR.reduce_scalars({}) == {}
+    assert float(PAR.reduce_tensor(torch.tensor(3.0))) == 3.0

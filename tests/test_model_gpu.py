@@ -129,8 +129,10 @@ def test_full_model_against_reference(arch, no_dropout):
     near(loss, fix["loss"], noise["loss"], "loss")
     loss.backward()
     # gradient norms: a structural check (a missing term is an O(1) error).  One perturbation run is a crude
-    # estimate of the reference's conditioning, so the floor is 3 %; parameters whose true gradient is zero
-    # (a bias feeding another BatchNorm) hold only rounding residue and are skipped by magnitude.
+    # estimate of the reference's conditioning and cannot see the model's kinks: a channel-argmax of the dynamic
+    # filters that flips under 1e-6 jitter of the decoder output moves fuse_coef / spat_filter.layer2 by 4.3 % / 3.9 %
+    # (both states measured, profiles/r02_determinism_udr18.txt), so the floor is 6 %; parameters whose true gradient
+    # is zero (a bias feeding another BatchNorm) hold only rounding residue and are skipped by magnitude.
     bad = []
     gmax = max(v["norm"] for v in fix["param_grads"].values() if v is not None)
     for n, p in model.named_parameters():
@@ -142,10 +144,10 @@ def test_full_model_against_reference(arch, no_dropout):
         gn = p.grad.norm().item()
         if ref["norm"] < 1e-5 * gmax:
             continue
-        tol = (3e-2 + 8.0 * noise["grad_norm_rel"][n]) * ref["norm"]
+        tol = (6e-2 + 8.0 * noise["grad_norm_rel"][n]) * ref["norm"]
         if abs(gn - ref["norm"]) > tol:
             bad.append((n, gn, ref["norm"], noise["grad_norm_rel"][n]))
-    assert not bad, bad[:8]
+    assert not bad, bad[:8]                  # (name, ours, reference, reference noise)
     sd = model.state_dict()
     for k, v in fix["bn_after"].items():
         near(sd[k], v, noise["bn_after"][k], k)
@@ -166,57 +168,102 @@ def test_eval_mode_and_dtypes():
 
 # bf16 statement for the BENCHMARKED configuration (bench.py: bf16 autocast for the stock-torch backbone and the dense
 # convolutions, channels_last backbone, SFConv transforms as bf16 DFT-by-GEMM, TF32 tcgen05 projections, fp32 hot-path
-# kernels) against the fp32 reference fixtures.  bf16 carries 8 mantissa bits (2^-9 = 2e-3 per rounding); through the
-# 32-block EfficientNet-B4 with train-mode BatchNorm on 4 samples the observed drift is a few 1e-2 relative, hence:
-#   per-sample losses / triplet features / loss: |err| <= 6e-2 * max|ref|     masks (bounded by 1): <= 6e-2 abs
-#   rec (tanh output in [-1,1], worst pixel of 4x3xRxR): <= 0.15 abs (observed 0.097; its mean error is what the
-#   `spatial` / `freq` losses above bound)     logits: <= 0.15 * max|ref| + 0.1 (the head sits behind every bf16 layer).
-BF16_REL, BF16_MASK_ABS, BF16_REC_ABS = 6e-2, 6e-2, 0.15
+# kernels).  bf16 carries 8 mantissa bits (2^-9 = 2e-3 per rounding) and the models normalise with train-mode batch /
+# instance statistics, so single elements can move a lot (a pixel of a low-variance InstanceNorm plane, a logit behind
+# a 4-sample BatchNorm1d) while every aggregate stays close.  The statement is therefore in RELATIVE L2 error
+# ||a - b|| / ||b|| per tensor (plus the absolute error of the scalar losses), stated twice:
+#   (1) against the fp32 REFERENCE fixtures (4 samples: the noisiest possible batch statistics);
+#   (2) against this repo's own fp32 path -- which the tests above pin to the reference at 1e-4 -- on 16 samples, where
+#       the batch statistics are what training sees.
+def _rel2(a, b):
+    a, b = a.detach().float().cpu().flatten(), b.detach().float().cpu().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
 
 
-@pytest.mark.parametrize("arch", ["eb4", "r18"])
-def test_bench_configuration_bf16_against_fp32_reference(arch, no_dropout):
-    from unidefense_b200 import ops
-    fix = torch.load(os.path.join(GOLDEN, f"full_{arch}.pt"), weights_only=False)
-    model = _build(arch, 5, False)
+def _bench_config(model):
     for part in ("backbone", "extractor", "emb_block1", "emb_block2"):      # bench.py --channels-last backbone
         if hasattr(model, part):
             getattr(model, part).to(memory_format=torch.channels_last)
-    x = P.tensor_for(f"in:full_x_{arch}", (fix["N"], 3, fix["R"], fix["R"]), "unit").cuda()
-    labels = fix["labels"].cuda()
+    return model
+
+
+def _bf16_forward(model, x):
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = True                                   # torch default, as in bench.py
     try:
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = model(x)
+            return model(x)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def _pass1_loss(out, labels, nr):
+    from unidefense_b200 import ops
     ld = out["loss_dict"]
-
-    bad, seen = [], []
-
-    def near(a, b, what, rel=BF16_REL, floor=0.0):
-        b = b.detach().float()
-        tol = rel * max(float(b.abs().max()), 1e-6) + floor
-        err = float((a.detach().float().cpu() - b).abs().max())
-        seen.append(f"{what}: {err:.3e} (tol {tol:.3e})")
-        if err > tol:
-            bad.append(f"{what}: max abs err {err:.3e} > {tol:.3e}")
-
-    near(ld["spatial"], fix["spatial"], "spatial")
-    near(ld["freq"], fix["freq"], "freq")
-    near(ld["freq_mask"], fix["freq_mask"], "freq_mask", 0.0, BF16_MASK_ABS)
-    near(ld["spat_mask"], fix["spat_mask"], "spat_mask", 0.0, BF16_MASK_ABS)
-    near(out["rec"][:, :, ::7, ::5], fix["rec_sample"], "rec", 0.0, BF16_REC_ABS)
-    for i, (a, b) in enumerate(zip(ld["triplet"], fix["triplet_feats"])):
-        near(a, b, f"triplet[{i}]")
-    near(out["cls_out"], fix["cls_out"], "cls_out", 0.15, 0.1)
-    nr = fix["N"] // 2
     tri = sum(ops.triplet_loss(f.float(), labels) for f in ld["triplet"])
-    loss = (ops.cross_entropy(out["cls_out"].float(), labels) + 0.1 * ld["freq_mask"].mean() + 0.1 * ld["spat_mask"].mean()
+    return (ops.cross_entropy(out["cls_out"].float(), labels) + 0.1 * ld["freq_mask"].mean() + 0.1 * ld["spat_mask"].mean()
             + 0.1 * tri + 0.1 * ld["spatial"][:nr].mean() + 1.0 * ld["freq"][:nr].mean())
-    near(loss, fix["loss"], "loss")
-    print(f"bf16 bench configuration vs fp32 reference ({arch}): " + "; ".join(seen))
-    assert not bad, "bf16 bench configuration: " + "; ".join(bad) + " | all: " + "; ".join(seen)
+
+
+# relative-L2 budgets: (vs reference fixtures, 4 samples), (vs own fp32 path, 16 samples)
+BF16_BUDGET = {"rec": (0.15, 0.06), "freq_mask": (0.10, 0.04), "spat_mask": (0.10, 0.04), "triplet": (0.06, 0.03),
+               "cls_out": (0.30, 0.10), "spatial": (0.03, 0.01), "freq": (0.03, 0.01), "loss": (0.10, 0.03)}
+
+
+def _bf16_report(pairs, which, arch, label):
+    bad, seen = [], []
+    for what, a, b in pairs:
+        err, tol = _rel2(a, b), BF16_BUDGET[what.split("[")[0]][which]
+        seen.append(f"{what} {err:.2e}/{tol:.0e}")
+        if not err <= tol:
+            bad.append(f"{what}: relative L2 error {err:.3e} > {tol:.1e}")
+    print(f"bf16 bench configuration vs {label} ({arch}), relative L2 error / budget: " + "; ".join(seen))
+    assert not bad, f"bf16 bench configuration vs {label}: " + "; ".join(bad) + " | all: " + "; ".join(seen)
+
+
+@pytest.mark.parametrize("arch", ["eb4", "r18"])
+def test_bench_configuration_bf16_against_fp32_reference(arch, no_dropout):
+    fix = torch.load(os.path.join(GOLDEN, f"full_{arch}.pt"), weights_only=False)
+    model = _bench_config(_build(arch, 5, False))
+    x = P.tensor_for(f"in:full_x_{arch}", (fix["N"], 3, fix["R"], fix["R"]), "unit").cuda()
+    labels = fix["labels"].cuda()
+    out = _bf16_forward(model, x)
+    ld = out["loss_dict"]
+    loss = _pass1_loss(out, labels, fix["N"] // 2)
+    pairs = [("spatial", ld["spatial"], fix["spatial"]), ("freq", ld["freq"], fix["freq"]),
+             ("freq_mask", ld["freq_mask"], fix["freq_mask"]), ("spat_mask", ld["spat_mask"], fix["spat_mask"]),
+             ("rec", out["rec"][:, :, ::7, ::5], fix["rec_sample"]), ("cls_out", out["cls_out"], fix["cls_out"]),
+             ("loss", loss, fix["loss"])]
+    pairs += [(f"triplet[{i}]", a, b) for i, (a, b) in enumerate(zip(ld["triplet"], fix["triplet_feats"]))]
+    _bf16_report(pairs, 0, arch, "the fp32 reference fixtures (N=4)")
     loss.backward()
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.requires_grad)
+
+
+@pytest.mark.parametrize("arch,res", [("eb4", 128), ("r18", 128)])
+def test_bench_configuration_bf16_against_own_fp32_path(arch, res, no_dropout):
+    n = 16
+    g = torch.Generator().manual_seed(77)
+    x = (torch.rand(n, 3, res, res, generator=g) * 2 - 1).cuda()
+    labels = torch.tensor([0] * (n // 2) + [1] * (n // 2)).cuda()
+    ref_model = _build(arch, 5, False)
+    ref = ref_model(x)
+    ref_loss = _pass1_loss(ref, labels, n // 2)
+    model = _bench_config(_build(arch, 5, False))
+    out = _bf16_forward(model, x)
+    loss = _pass1_loss(out, labels, n // 2)
+    a, b = out["loss_dict"], ref["loss_dict"]
+    pairs = [("spatial", a["spatial"], b["spatial"]), ("freq", a["freq"], b["freq"]), ("freq_mask", a["freq_mask"], b["freq_mask"]),
+             ("spat_mask", a["spat_mask"], b["spat_mask"]), ("rec", out["rec"], ref["rec"]), ("cls_out", out["cls_out"], ref["cls_out"]),
+             ("loss", loss, ref_loss)]
+    pairs += [(f"triplet[{i}]", u, v) for i, (u, v) in enumerate(zip(a["triplet"], b["triplet"]))]
+    _bf16_report(pairs, 1, arch, "this repo's fp32 path (N=16)")
+    # gradients: direction and size of the flat parameter gradient
+    loss.backward()
+    ref_loss.backward()
+    ga = torch.cat([p.grad.float().flatten() for p in model.parameters() if p.grad is not None])
+    gb = torch.cat([p.grad.float().flatten() for p in ref_model.parameters() if p.grad is not None])
+    cos = float(torch.dot(ga, gb) / (ga.norm() * gb.norm()))
+    ratio = float(ga.norm() / gb.norm())
+    print(f"bf16 vs fp32 flat parameter gradient ({arch}): cosine {cos:.4f}, norm ratio {ratio:.4f}")
+    assert cos > 0.95 and 0.85 < ratio < 1.15, (cos, ratio)

@@ -18,6 +18,7 @@
 // The forward can also emit the per-plane mean of y (the triplet features dec_out.mean([-2,-1]),
 // model/unidefense.py:232-236) for free; the backward accepts its gradient.
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 
 #include "../../include/unidefense_b200.h"
 #include "ud_common.cuh"
@@ -153,7 +154,47 @@ __device__ __forceinline__ float ia_fold_sum(const float (*slots)[K], int k, int
   return ud_warp_sum(v);
 }
 
-// Slot validity of a lane.  A warp's slab of `len` float4 is read lane-strided: slot i of lane l is element
+// ---- I/O vector types: fp32 planes move as float4 (4 elements), bf16 planes as uint4 (8 elements) -------------
+// All arithmetic and the statistics are fp32 either way; a bf16 store rounds to nearest even, exactly what the
+// reference-side `.to(torch.bfloat16)` around an fp32 kernel would do (so the bf16 entry points are bit-identical to
+// cast -> fp32 kernel -> cast, minus the two casting passes over HBM).
+template <class IO>
+struct IaVec;
+template <>
+struct IaVec<float> {
+  typedef float4 V;
+  static constexpr int E = 4;
+  static __device__ __forceinline__ void load(const V* p, float (&f)[4]) {
+    const float4 t = __ldcs(p);
+    f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(V* p, const float (&f)[4]) { *p = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <>
+struct IaVec<__nv_bfloat16> {
+  typedef uint4 V;
+  static constexpr int E = 8;
+  static __device__ __forceinline__ void load(const V* p, float (&f)[8]) {
+    const uint4 t = __ldcs(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                      // bf16 -> fp32 is a 16-bit shift
+      f[2 * j] = __uint_as_float(w[j] << 16);
+      f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(V* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);   // .x (low half) = first element
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *p = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// Slot validity of a lane.  A warp's slab of `len` vectors is read lane-strided: slot i of lane l is vector
 // i*32 + l.  FAST (warp-uniform: the slab fills all but possibly the last of the VPT slots -- every shape of the
 // shipped configurations) makes slots 0..VPT-2 unconditional at compile time and leaves ONE runtime predicate for the
 // last slot, so the unrolled body carries no per-slot compare/branch/address arithmetic (which, with the range-checked
@@ -164,36 +205,49 @@ __device__ __forceinline__ bool ia_ok(int i, int lane, int len, bool last_ok) {
   return i * 32 + lane < len;
 }
 
-template <bool CLUSTER, int ACT, bool WANT_MEAN, int VPT, bool FAST>
-__device__ __forceinline__ void ia_fwd_body(const float4* __restrict__ xl, float4* __restrict__ yl, int lane, int len,
+template <class IO, bool CLUSTER, int ACT, bool WANT_MEAN, int VPT, bool FAST>
+__device__ __forceinline__ void ia_fwd_body(const typename IaVec<IO>::V* __restrict__ xl,
+                                            typename IaVec<IO>::V* __restrict__ yl, int lane, int len,
                                             float (*slots)[3], float (*yslots)[1], const IaGeom& ge, int cs, float g,
                                             float b, float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                             float* __restrict__ ymean_out) {
+  constexpr int E = IaVec<IO>::E;
   const bool last_ok = (VPT - 1) * 32 + lane < len;
-  float4 v[VPT];
+  float v[VPT][E];
   int nv = 0;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
-      v[i] = __ldcs(xl + i * 32);
+      IaVec<IO>::load(xl + i * 32, v[i]);
       ++nv;
     } else {
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[i][e] = 0.f;
     }
   }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int i = 0; i < VPT; ++i) {
+    float t = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; e += 2) t += v[i][e] + v[i][e + 1];
+    s += t;
+  }
   // thread-local two-pass statistics, then one merge tree
   IaStat st;
-  st.n = 4.f * (float)nv;
+  st.n = (float)(E * nv);
   st.mean = nv ? s * __frcp_rn(st.n) : 0.f;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
-      const float a = v[i].x - st.mean, bq = v[i].y - st.mean, c = v[i].z - st.mean, d = v[i].w - st.mean;
-      q += (a * a + bq * bq) + (c * c + d * d);
+      float t = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float d = v[i][e] - st.mean;
+        t = fmaf(d, d, t);
+      }
+      q += t;
     }
   }
   st.m2 = q;
@@ -208,13 +262,14 @@ __device__ __forceinline__ void ia_fwd_body(const float4* __restrict__ xl, float
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
-      float4 o;
-      o.x = ia_act<ACT>(fmaf(v[i].x, a_, b_));
-      o.y = ia_act<ACT>(fmaf(v[i].y, a_, b_));
-      o.z = ia_act<ACT>(fmaf(v[i].z, a_, b_));
-      o.w = ia_act<ACT>(fmaf(v[i].w, a_, b_));
-      if (WANT_MEAN) ys += (o.x + o.y) + (o.z + o.w);
-      yl[i * 32] = o;
+      float o[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) o[e] = ia_act<ACT>(fmaf(v[i][e], a_, b_));
+      if (WANT_MEAN) {
+#pragma unroll
+        for (int e = 0; e < E; e += 2) ys += o[e] + o[e + 1];
+      }
+      IaVec<IO>::store(yl + i * 32, o);
     }
   }
   const bool writer = ge.live && ge.wsub == 0 && lane == 0;
@@ -231,48 +286,51 @@ __device__ __forceinline__ void ia_fwd_body(const float4* __restrict__ xl, float
   }
 }
 
-template <bool CLUSTER, int ACT, bool WANT_MEAN, int VPT>
+// EV = vectors per plane (HW / 4 for fp32, HW / 8 for bf16)
+template <class IO, bool CLUSTER, int ACT, bool WANT_MEAN, int VPT>
 __global__ void __launch_bounds__(IA_THREADS, 4)
-ia_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-              float4* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-              float* __restrict__ ymean_out, int planes, int C, int E4, int G, int cs, float eps) {
+ia_fwd_kernel(const typename IaVec<IO>::V* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              typename IaVec<IO>::V* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+              float* __restrict__ ymean_out, int planes, int C, int EV, int G, int cs, float eps) {
   __shared__ float slots[IA_MAX_CS * IA_WARPS][3];
   __shared__ float yslots[IA_MAX_CS * IA_WARPS][1];
   const IaGeom ge = ia_geom<CLUSTER>(planes, G, cs);
   const int lane = threadIdx.x & 31;
-  const int per_w = (E4 + ge.nw - 1) / ge.nw;
+  const int per_w = (EV + ge.nw - 1) / ge.nw;
   const int beg = ge.wsub * per_w;
-  const int len = ge.live ? max(min(E4, beg + per_w) - beg, 0) : 0;     // float4 of this warp's slab (<= VPT*32)
+  const int len = ge.live ? max(min(EV, beg + per_w) - beg, 0) : 0;     // vectors of this warp's slab (<= VPT*32)
   const int pl = ge.live ? ge.plane : 0;
-  const float4* xl = x + (long long)pl * E4 + beg + lane;
-  float4* yl = y + (long long)pl * E4 + beg + lane;
+  const typename IaVec<IO>::V* xl = x + (long long)pl * EV + beg + lane;
+  typename IaVec<IO>::V* yl = y + (long long)pl * EV + beg + lane;
   const int ch = pl % C;
   const float g = gamma ? __ldg(gamma + ch) : 1.f;
   const float b = beta ? __ldg(beta + ch) : 0.f;
   // both branches run the same barriers / cluster syncs, so a CTA (cluster) may mix them
   if (len > (VPT - 1) * 32)
-    ia_fwd_body<CLUSTER, ACT, WANT_MEAN, VPT, true>(xl, yl, lane, len, slots, yslots, ge, cs, g, b, eps, mean_out, rstd_out,
-                                                    ymean_out);
+    ia_fwd_body<IO, CLUSTER, ACT, WANT_MEAN, VPT, true>(xl, yl, lane, len, slots, yslots, ge, cs, g, b, eps, mean_out,
+                                                        rstd_out, ymean_out);
   else
-    ia_fwd_body<CLUSTER, ACT, WANT_MEAN, VPT, false>(xl, yl, lane, len, slots, yslots, ge, cs, g, b, eps, mean_out, rstd_out,
-                                                     ymean_out);
+    ia_fwd_body<IO, CLUSTER, ACT, WANT_MEAN, VPT, false>(xl, yl, lane, len, slots, yslots, ge, cs, g, b, eps, mean_out,
+                                                         rstd_out, ymean_out);
 }
 
-template <bool CLUSTER, int ACT, int VPT, bool FAST>
-__device__ __forceinline__ void ia_bwd_body(const float4* __restrict__ xl, const float4* __restrict__ gl,
-                                            float4* __restrict__ ol, int lane, int len, float (*slots)[2],
+template <class IO, bool CLUSTER, int ACT, int VPT, bool FAST>
+__device__ __forceinline__ void ia_bwd_body(const typename IaVec<IO>::V* __restrict__ xl,
+                                            const typename IaVec<IO>::V* __restrict__ gl,
+                                            typename IaVec<IO>::V* __restrict__ ol, int lane, int len, float (*slots)[2],
                                             const IaGeom& ge, int cs, float g, float b, float mu, float rstd, float gadd,
                                             float invE, float* __restrict__ s1_out, float* __restrict__ s2_out) {
+  constexpr int E = IaVec<IO>::E;
   const bool last_ok = (VPT - 1) * 32 + lane < len;
-  float4 xh[VPT], gz[VPT];
+  float xh[VPT][E], gz[VPT][E];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {   // all loads in flight before any math
     if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
-      xh[i] = __ldcs(xl + i * 32);
-      gz[i] = __ldcs(gl + i * 32);
+      IaVec<IO>::load(xl + i * 32, xh[i]);
+      IaVec<IO>::load(gl + i * 32, gz[i]);
     } else {
-      xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int e = 0; e < E; ++e) xh[i][e] = gz[i][e] = 0.f;
     }
   }
   float s1 = 0.f, s2 = 0.f;
@@ -280,17 +338,18 @@ __device__ __forceinline__ void ia_bwd_body(const float4* __restrict__ xl, const
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
-      float4 h, z;
-      h.x = fmaf(xh[i].x, rstd, nmr); h.y = fmaf(xh[i].y, rstd, nmr);
-      h.z = fmaf(xh[i].z, rstd, nmr); h.w = fmaf(xh[i].w, rstd, nmr);
-      z.x = (gz[i].x + gadd) * ia_act_grad<ACT>(fmaf(h.x, g, b));
-      z.y = (gz[i].y + gadd) * ia_act_grad<ACT>(fmaf(h.y, g, b));
-      z.z = (gz[i].z + gadd) * ia_act_grad<ACT>(fmaf(h.z, g, b));
-      z.w = (gz[i].w + gadd) * ia_act_grad<ACT>(fmaf(h.w, g, b));
-      s1 += (z.x + z.y) + (z.z + z.w);
-      s2 += (z.x * h.x + z.y * h.y) + (z.z * h.z + z.w * h.w);
-      xh[i] = h;
-      gz[i] = z;
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float h = fmaf(xh[i][e], rstd, nmr);
+        const float z = (gz[i][e] + gadd) * ia_act_grad<ACT>(fmaf(h, g, b));
+        t1 += z;
+        t2 = fmaf(z, h, t2);
+        xh[i][e] = h;
+        gz[i][e] = z;
+      }
+      s1 += t1;
+      s2 += t2;
     }
   }
   s1 = ud_warp_sum(s1);
@@ -308,12 +367,10 @@ __device__ __forceinline__ void ia_bwd_body(const float4* __restrict__ xl, const
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     if (ia_ok<FAST, VPT>(i, lane, len, last_ok)) {
-      float4 o;
-      o.x = k * (gz[i].x - m1 - xh[i].x * m2);
-      o.y = k * (gz[i].y - m1 - xh[i].y * m2);
-      o.z = k * (gz[i].z - m1 - xh[i].z * m2);
-      o.w = k * (gz[i].w - m1 - xh[i].w * m2);
-      ol[i * 32] = o;
+      float o[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) o[e] = k * (gz[i][e] - m1 - xh[i][e] * m2);
+      IaVec<IO>::store(ol + i * 32, o);
     }
   }
   if (ge.live && ge.wsub == 0 && lane == 0) {
@@ -322,32 +379,32 @@ __device__ __forceinline__ void ia_bwd_body(const float4* __restrict__ xl, const
   }
 }
 
-template <bool CLUSTER, int ACT, int VPT>
+template <class IO, bool CLUSTER, int ACT, int VPT>
 __global__ void __launch_bounds__(IA_THREADS, 4)
-ia_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const float* __restrict__ gamma,
-              const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd_in,
-              const float* __restrict__ g_ymean, float4* __restrict__ gx, float* __restrict__ s1_out,
-              float* __restrict__ s2_out, int planes, int C, int E4, int G, int cs) {
+ia_bwd_kernel(const typename IaVec<IO>::V* __restrict__ x, const typename IaVec<IO>::V* __restrict__ gy,
+              const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+              const float* __restrict__ rstd_in, const float* __restrict__ g_ymean, typename IaVec<IO>::V* __restrict__ gx,
+              float* __restrict__ s1_out, float* __restrict__ s2_out, int planes, int C, int EV, int G, int cs) {
   __shared__ __align__(8) float slots[IA_MAX_CS * IA_WARPS][2];
   const IaGeom ge = ia_geom<CLUSTER>(planes, G, cs);
   const int lane = threadIdx.x & 31;
-  const int per_w = (E4 + ge.nw - 1) / ge.nw;
+  const int per_w = (EV + ge.nw - 1) / ge.nw;
   const int beg = ge.wsub * per_w;
-  const int len = ge.live ? max(min(E4, beg + per_w) - beg, 0) : 0;
+  const int len = ge.live ? max(min(EV, beg + per_w) - beg, 0) : 0;
   const int pl = ge.live ? ge.plane : 0;
-  const long long off = (long long)pl * E4 + beg + lane;
+  const long long off = (long long)pl * EV + beg + lane;
   const int ch = pl % C;
   const float g = gamma ? __ldg(gamma + ch) : 1.f;
   const float b = beta ? __ldg(beta + ch) : 0.f;
   const float mu = mean[pl], rstd = rstd_in[pl];
-  const float invE = 1.f / (4.f * (float)E4);
+  const float invE = 1.f / ((float)IaVec<IO>::E * (float)EV);
   const float gadd = g_ymean ? g_ymean[pl] * invE : 0.f;  // d mean(y) term
   if (len > (VPT - 1) * 32)
-    ia_bwd_body<CLUSTER, ACT, VPT, true>(x + off, gy + off, gx + off, lane, len, slots, ge, cs, g, b, mu, rstd, gadd, invE,
-                                         s1_out, s2_out);
+    ia_bwd_body<IO, CLUSTER, ACT, VPT, true>(x + off, gy + off, gx + off, lane, len, slots, ge, cs, g, b, mu, rstd, gadd,
+                                             invE, s1_out, s2_out);
   else
-    ia_bwd_body<CLUSTER, ACT, VPT, false>(x + off, gy + off, gx + off, lane, len, slots, ge, cs, g, b, mu, rstd, gadd,
-                                          invE, s1_out, s2_out);
+    ia_bwd_body<IO, CLUSTER, ACT, VPT, false>(x + off, gy + off, gx + off, lane, len, slots, ge, cs, g, b, mu, rstd, gadd,
+                                              invE, s1_out, s2_out);
 }
 
 // ---- generic fallback: any plane size (odd E, huge planes): one CTA per plane, re-reads hit L1/L2 ----

@@ -245,3 +245,38 @@ def convert_sync_batchnorm(module, process_group=None):
     for name, child in module.named_children():
         out.add_module(name, convert_sync_batchnorm(child, process_group))
     return out
+
+
+# ---- harness-side synchronisation -----------------------------------------------------------
+def reduce_tensor(t, group=None):
+    """Drop-in for the reference's utils/misc.py:18-22 (`all_reduce` then divide by the world size)."""
+    rt = t.detach().clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(rt, group=group)
+        rt /= float(dist.get_world_size(group))
+    return rt
+
+
+def reduce_scalars(values, group=None):
+    """The logging tail of the reference's training loops (engine/forgery_engine.py:279-287, ocim_engine.py:271-279,
+    uniattack_engine.py:333-341) calls `reduce_tensor(v).item()` once per logged loss and once for the accuracy: ~10
+    latency-bound all-reduces, each followed by a host synchronisation, every step.  This packs every scalar of
+    `values` (a dict name -> 0-d / 1-element tensor or float) into ONE tensor, averages it over the ranks with ONE
+    all-reduce and reads it back with ONE device-to-host copy.  Returns {name: float} with exactly the numbers the
+    per-key calls produce (same fp32 sum over ranks, same division)."""
+    names = list(values)
+    if not names:
+        return {}
+    dev = next((v.device for v in values.values() if torch.is_tensor(v)), torch.device("cpu"))
+    packed = torch.stack([(v.detach().reshape(-1)[0] if torch.is_tensor(v) else torch.tensor(float(v))).to(dev, torch.float32)
+                          for v in values.values()])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, group=group)
+        packed /= float(dist.get_world_size(group))
+    host = packed.tolist()                     # the step's only host synchronisation for logging
+    return dict(zip(names, host))
+
+
+def logged_losses(out_dict):
+    """The keys the reference loops log: every entry of the engine's return dict whose name contains "loss"."""
+    return {k: v for k, v in out_dict.items() if "loss" in k}
