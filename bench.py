@@ -86,13 +86,14 @@ def decoder_planes(arch, R):
             (32, 8 * f)], 8 * f
 
 
-def alg_bytes(arch, N, R, n_real):
-    """Compulsory fp32 HBM bytes per step of each op group: every tensor crossing the group boundary read
-    once + written once."""
+def alg_bytes(arch, N, R, n_real, act_bytes=4):
+    """Compulsory HBM bytes per step of each op group: every tensor crossing the group boundary read once + written
+    once.  fp32 everywhere except the decoder epilogues, whose activations are `act_bytes` wide (2 under bf16 autocast:
+    the bf16 in/out kernels; SURVEY.md §8d "bf16 activations halve G2")."""
     planes, h = decoder_planes(arch, R)
     E = sum(c * s * s for c, s in planes)
     img, dec = 3 * R * R * 4, 3 * h * h * 4
-    return {"in_act_fwd": N * 2 * E * 4, "in_act_bwd": N * 3 * E * 4,
+    return {"in_act_fwd": N * 2 * E * act_bytes, "in_act_bwd": N * 3 * E * act_bytes,
             "tanh_fwd": N * 2 * dec, "tanh_bwd": N * 3 * dec,
             "recon_tail_fwd": N * (dec + 2 * img) + 8 * N,
             "recon_tail_bwd": n_real * (dec + img) + N * dec}
@@ -782,7 +783,8 @@ def run_ours(args):
 
     if rank == 0:
         pk, pk_kind = peaks()
-        ab = alg_bytes(arch, nb, res, nr)
+        act_bytes = 2 if args.dtype == "bf16" else 4
+        ab = alg_bytes(arch, nb, res, nr, act_bytes)
         ops_ms = {k: v[1] / prof_steps for k, v in prof.items()}
         timed = {k: (ab[k] / (ops_ms[k] * 1e-3) / 1e9) for k in ab if k in ops_ms and ops_ms[k] > 0}
         dom = max((k for k in ops_ms if k in ab), key=lambda k: ops_ms[k], default=None)
@@ -799,6 +801,9 @@ def run_ours(args):
         comm_ms = ops_ms.get("comm_gather", 0.0)
         hot_ms = sum(ops_ms.values()) - sf_ms - dense_ms - comm_ms
         mbs = RECON_MB_PER_SAMPLE.get((arch, res))
+        if mbs and act_bytes == 2:               # SURVEY's figure counts fp32 epilogue activations: take half of G2 off
+            f32 = alg_bytes(arch, 1, res, 1, 4)
+            mbs = round(mbs - 0.5 * (f32["in_act_fwd"] + f32["in_act_bwd"]) / 1e6, 2)
         line = {"metric": METRIC, "value": round(nb * world / (ms * 1e-3), 2), "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
@@ -807,7 +812,9 @@ def run_ours(args):
                                         if args.two_pass else
                                         f"UniDefense {name} train step (fwd + engine pass-1 loss + bwd + AdamW amsgrad), ")
                                        + f"{res}x{res}, per-GPU batch {nb}, random init",
-                           "hot_path_dtype": "f32", "backbone": f"stock torch, {args.dtype} autocast"
+                           "hot_path_dtype": "f32" if act_bytes == 4 else
+                                             "f32 arithmetic; decoder epilogues bf16 in / bf16 out (algorithmic bytes counted at 2 B)",
+                           "backbone": f"stock torch, {args.dtype} autocast"
                                        + (f", channels_last ({args.channels_last})" if args.channels_last != "none" else ""),
                            "parallelism": f"dp{world}" + ((" (flat-gradient NCCL all-reduce + SyncBatchNorm over NVLink peer memory)"
                                                             if flat is not None else
@@ -830,7 +837,7 @@ def run_ours(args):
                              "ops_ms_per_step": {k: round(v, 4) for k, v in sorted(ops_ms.items(), key=lambda kv: -kv[1])},
                              "ops_gbs": {k: round(v, 1) for k, v in timed.items()}}}
         if recon_ms is not None:
-            mb = RECON_MB_PER_SAMPLE.get((arch, res))
+            mb = mbs                                 # (bf16-adjusted like hot_path.alg_mb_per_sample)
             kern_ms = sum(recon_prof.values())
             line["recon_path"] = {
                 "what": "isolated recon path fwd+bwd on cached backbone features (decoder incl. cuDNN convs, attention, "

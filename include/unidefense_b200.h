@@ -92,6 +92,16 @@ UD_API int ud_in_act_bwd(const float* x, const float* gy, const float* gamma, co
                          const float* mean, const float* rstd, const float* g_ymean, float* gx, float* ggamma,
                          float* gbeta, void* ws, size_t ws_bytes, int N, int C, int HW, int act,
                          cudaStream_t stream);
+/* bf16 in / bf16 out variants (SURVEY §8b "bf16 in/out variants with fp32 accumulation"): x, y, gy, gx are bf16
+ * [N,C,HW] (torch.bfloat16 storage, passed as void*); statistics, affine parameters, ymean and all arithmetic stay fp32;
+ * stores round to nearest even.  Under bf16 autocast the decoder convolutions emit and consume bf16, so these calls
+ * remove the fp32 <-> bf16 casting passes the reference composition makes around every InstanceNorm
+ * (bit-identical to cast -> fp32 kernel -> cast).                                                         */
+UD_API int ud_in_act_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                              float* ymean, int N, int C, int HW, float eps, int act, cudaStream_t stream);
+UD_API int ud_in_act_bwd_bf16(const void* x, const void* gy, const float* gamma, const float* beta, const float* mean,
+                              const float* rstd, const float* g_ymean, void* gx, float* ggamma, float* gbeta, void* ws,
+                              size_t ws_bytes, int N, int C, int HW, int act, cudaStream_t stream);
 /* nn.Tanh decoder output (model/unidefense.py:101, :307, :499). */
 UD_API int ud_tanh_fwd(const float* x, float* y, long long n, cudaStream_t stream);
 UD_API int ud_tanh_bwd(const float* y, const float* gy, float* gx, long long n, cudaStream_t stream);

@@ -80,14 +80,16 @@ def main():
             torch.autograd.backward([sp, fr], [0.1 * g, g], retain_graph=True)
         ms, best = timeit(bwd, a.iters, flush)
         report("recon_tail_bwd (real half)", ms, best, ab["recon_tail_bwd"])
-    if "in_act" in want:
+    for io, tag, nby in ((torch.float32, "in_act", 4), (torch.bfloat16, "in_act_bf16", 2)):
+        if tag not in want:
+            continue
         for c, s in sorted(set(planes)):
-            x = torch.randn(nb, c, s, s, device=dev, requires_grad=True)
+            x = torch.randn(nb, c, s, s, device=dev).to(io).requires_grad_()
             gamma = torch.rand(c, device=dev, requires_grad=True)
             beta = torch.randn(c, device=dev, requires_grad=True)
             E = nb * c * s * s
             ms, best = timeit(lambda: ops.in_act(x, gamma, beta, act), a.iters, flush)
-            report(f"in_act_fwd {c}x{s}x{s}", ms, best, 2 * E * 4)
+            report(f"{tag}_fwd {c}x{s}x{s}", ms, best, 2 * E * nby)
             y = ops.in_act(x, gamma, beta, act)
             gy = torch.randn_like(y)
 
@@ -95,7 +97,7 @@ def main():
                 x.grad = None
                 y.backward(gy, retain_graph=True)
             ms, best = timeit(bwd, a.iters, flush)
-            report(f"in_act_bwd {c}x{s}x{s}", ms, best, 3 * E * 4)
+            report(f"{tag}_bwd {c}x{s}x{s}", ms, best, 3 * E * nby)
     if "tanh" in want:
         x = torch.randn(nb, 3, h, h, device=dev, requires_grad=True)
         ms, best = timeit(lambda: ops.tanh(x), a.iters, flush)

@@ -34,6 +34,8 @@ SIGNATURES = {
     "ud_in_act_fwd": (c_i, [c_p] * 7 + [c_i] * 3 + [c_f, c_i, c_p]),
     "ud_in_act_bwd_workspace_bytes": (c_sz, [c_i, c_i]),
     "ud_in_act_bwd": (c_i, [c_p] * 11 + [c_sz] + [c_i] * 4 + [c_p]),
+    "ud_in_act_fwd_bf16": (c_i, [c_p] * 7 + [c_i] * 3 + [c_f, c_i, c_p]),
+    "ud_in_act_bwd_bf16": (c_i, [c_p] * 11 + [c_sz] + [c_i] * 4 + [c_p]),
     "ud_tanh_fwd": (c_i, [c_p, c_p, ctypes.c_longlong, c_p]),
     "ud_tanh_bwd": (c_i, [c_p, c_p, c_p, ctypes.c_longlong, c_p]),
     "ud_bilinear_ac_fwd": (c_i, [c_p, c_p] + [c_i] * 5 + [c_p]),
@@ -164,7 +166,8 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def require_cuda_f32(*tensors):
+def require_cuda_f32(*tensors, also=()):
+    """`also`: extra dtypes an entry point accepts for these tensors (the bf16 I/O variants)."""
     for t in tensors:
         if t is None:
             continue
@@ -174,7 +177,7 @@ def require_cuda_f32(*tensors):
             raise RuntimeError(f"tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}: "
                                "the stream, workspace and twiddle tables belong to the current device "
                                "(call torch.cuda.set_device(local_rank) as the reference engines do)")
-        if t.dtype != torch.float32:
+        if t.dtype != torch.float32 and t.dtype not in also:
             raise RuntimeError(f"unidefense_b200 kernels are fp32; got {t.dtype}")
         if not t.is_contiguous():
             raise RuntimeError("unidefense_b200 kernels need contiguous tensors")

@@ -408,20 +408,26 @@ ia_bwd_kernel(const typename IaVec<IO>::V* __restrict__ x, const typename IaVec<
 }
 
 // ---- generic fallback: any plane size (odd E, huge planes): one CTA per plane, re-reads hit L1/L2 ----
+__device__ __forceinline__ float ia_ld(const float* p) { return *p; }
+__device__ __forceinline__ float ia_ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void ia_st(float* p, float v) { *p = v; }
+__device__ __forceinline__ void ia_st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <class IO>
 __global__ void __launch_bounds__(IA_THREADS)
-ia_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+ia_fwd_generic_kernel(const IO* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      IO* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                       float* __restrict__ ymean_out, int C, int E, float eps, int act) {
   __shared__ float red[33];
   const int plane = blockIdx.x;
-  const float* xp = x + (long long)plane * E;
-  float* yp = y + (long long)plane * E;
+  const IO* xp = x + (long long)plane * E;
+  IO* yp = y + (long long)plane * E;
   float s = 0.f;
-  for (int i = threadIdx.x; i < E; i += blockDim.x) s += xp[i];
+  for (int i = threadIdx.x; i < E; i += blockDim.x) s += ia_ld(xp + i);
   const float mu = ud_block_sum(s, red) / (float)E;
   float q = 0.f;
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    const float d = xp[i] - mu;
+    const float d = ia_ld(xp + i) - mu;
     q += d * d;
   }
   const float rstd = rsqrtf(ud_block_sum(q, red) / (float)E + eps);
@@ -430,9 +436,9 @@ ia_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ gam
   const float a_ = g * rstd, b_ = b - mu * g * rstd;
   float ys = 0.f;
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    const float o = ud_act_fwd(fmaf(xp[i], a_, b_), act);
+    const float o = ud_act_fwd(fmaf(ia_ld(xp + i), a_, b_), act);
     ys += o;
-    yp[i] = o;
+    ia_st(yp + i, o);
   }
   if (ymean_out != nullptr) {
     const float t = ud_block_sum(ys, red) / (float)E;
@@ -444,10 +450,11 @@ ia_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ gam
   }
 }
 
+template <class IO>
 __global__ void __launch_bounds__(IA_THREADS)
-ia_bwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ gamma,
+ia_bwd_generic_kernel(const IO* __restrict__ x, const IO* __restrict__ gy, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ mean,
-                      const float* __restrict__ rstd_in, const float* __restrict__ g_ymean, float* __restrict__ gx,
+                      const float* __restrict__ rstd_in, const float* __restrict__ g_ymean, IO* __restrict__ gx,
                       float* __restrict__ s1_out, float* __restrict__ s2_out, int C, int E, int act) {
   __shared__ float red[33];
   const int plane = blockIdx.x;
@@ -458,8 +465,8 @@ ia_bwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ gy,
   const float gadd = g_ymean ? g_ymean[plane] / (float)E : 0.f;
   float s1 = 0.f, s2 = 0.f;
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    const float h = (x[base + i] - mu) * rstd;
-    const float z = (gy[base + i] + gadd) * ud_act_grad(fmaf(h, g, b), act);
+    const float h = (ia_ld(x + base + i) - mu) * rstd;
+    const float z = (ia_ld(gy + base + i) + gadd) * ud_act_grad(fmaf(h, g, b), act);
     s1 += z;
     s2 += z * h;
   }
@@ -467,9 +474,9 @@ ia_bwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ gy,
   const float S2 = ud_block_sum(s2, red);
   const float m1 = S1 / (float)E, m2 = S2 / (float)E, k = g * rstd;
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    const float h = (x[base + i] - mu) * rstd;
-    const float z = (gy[base + i] + gadd) * ud_act_grad(fmaf(h, g, b), act);
-    gx[base + i] = k * (z - m1 - h * m2);
+    const float h = (ia_ld(x + base + i) - mu) * rstd;
+    const float z = (ia_ld(gy + base + i) + gadd) * ud_act_grad(fmaf(h, g, b), act);
+    ia_st(gx + base + i, k * (z - m1 - h * m2));
   }
   if (threadIdx.x == 0) {
     s1_out[plane] = S1;
@@ -491,12 +498,12 @@ __global__ void ia_param_grad_kernel(const float* __restrict__ s1, const float* 
   if (gbeta) gbeta[c] = b;
 }
 
-// smallest power-of-two warp count nw (<= 64) whose per-warp slab fits vmax float4 per lane
-static bool ia_pick(int E, int vmax, int* G, int* cs, int* vpt) {
-  if (E % 4 != 0) return false;
-  const int E4 = E / 4;
+// smallest power-of-two warp count nw (<= 64) whose per-warp slab fits vmax vectors (of epv elements) per lane
+static bool ia_pick(int E, int epv, int vmax, int* G, int* cs, int* vpt) {
+  if (E % epv != 0) return false;
+  const int EV = E / epv;
   for (int nw = 1; nw <= IA_MAX_CS * IA_WARPS; nw *= 2) {
-    const int per = (E4 + nw - 1) / nw;
+    const int per = (EV + nw - 1) / nw;
     const int v = (per + 31) / 32;
     if (v <= vmax) {
       *G = nw <= IA_WARPS ? nw : IA_WARPS;
@@ -539,27 +546,34 @@ static int ia_launch(K kernel, int blocks, int cs, cudaStream_t stream, Args... 
   return UD_OK;
 }
 
-extern "C" int ud_in_act_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
-                             float* rstd, float* ymean, int N, int C, int HW, float eps, int act,
-                             cudaStream_t stream) {
+// registers: a slot holds 4 (fp32) or 8 (bf16) values per lane -> 9/5 slots forward, 5/3 (x and gy) backward
+template <class IO> struct IaBudget;
+template <> struct IaBudget<float> { static constexpr int FWD = 9, FWD_SMALL = 5, BWD = 5; };
+template <> struct IaBudget<__nv_bfloat16> { static constexpr int FWD = 5, FWD_SMALL = 3, BWD = 3; };
+
+template <class IO>
+static int ia_fwd_impl(const IO* x, const float* gamma, const float* beta, IO* y, float* mean, float* rstd, float* ymean,
+                       int N, int C, int HW, float eps, int act, cudaStream_t stream) {
   UD_REQUIRE(N >= 0 && C >= 1 && HW >= 1, UD_ERR_INVALID, "in_act_fwd: bad shape N=%d C=%d HW=%d", N, C, HW);
   UD_REQUIRE(act >= UD_ACT_NONE && act <= UD_ACT_SWISH, UD_ERR_INVALID, "in_act_fwd: bad activation %d", act);
   if (N == 0) return UD_OK;
   UD_REQUIRE(x && y && mean && rstd, UD_ERR_INVALID, "in_act_fwd: null pointer");
+  typedef typename IaVec<IO>::V V;
+  constexpr int EPV = IaVec<IO>::E;
   const int planes = N * C;
   int cs = 1, vpt = 1;
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
   int G = 1;
-  if (aligned && ia_pick(HW, IA_VMAX_FWD, &G, &cs, &vpt)) {
-    const float4* x4 = reinterpret_cast<const float4*>(x);
-    float4* y4 = reinterpret_cast<float4*>(y);
-#define IA_FWD_V(CL, WM, BLOCKS, V)                                                                                  \
-  IA_ACT_SWITCH(act, return ia_launch(ia_fwd_kernel<CL, ACT_, WM, V>, BLOCKS, cs, stream, x4, gamma, beta, y4, mean, rstd, \
-                                      ymean, planes, C, HW / 4, G, cs, eps))
-#define IA_FWD(CL, WM, BLOCKS)                       \
-  do {                                               \
-    if (vpt <= 5) IA_FWD_V(CL, WM, BLOCKS, 5);       \
-    IA_FWD_V(CL, WM, BLOCKS, IA_VMAX_FWD);           \
+  if (aligned && ia_pick(HW, EPV, IaBudget<IO>::FWD, &G, &cs, &vpt)) {
+    const V* xv = reinterpret_cast<const V*>(x);
+    V* yv = reinterpret_cast<V*>(y);
+#define IA_FWD_V(CL, WM, BLOCKS, VP)                                                                                     \
+  IA_ACT_SWITCH(act, return ia_launch(ia_fwd_kernel<IO, CL, ACT_, WM, VP>, BLOCKS, cs, stream, xv, gamma, beta, yv, mean, \
+                                      rstd, ymean, planes, C, HW / EPV, G, cs, eps))
+#define IA_FWD(CL, WM, BLOCKS)                                                  \
+  do {                                                                          \
+    if (vpt <= IaBudget<IO>::FWD_SMALL) IA_FWD_V(CL, WM, BLOCKS, IaBudget<IO>::FWD_SMALL); \
+    IA_FWD_V(CL, WM, BLOCKS, IaBudget<IO>::FWD);                                \
   } while (0)
     if (cs == 1 && ymean) IA_FWD(false, true, ud_cdiv(planes, IA_WARPS / G));
     if (cs == 1) IA_FWD(false, false, ud_cdiv(planes, IA_WARPS / G));
@@ -568,16 +582,28 @@ extern "C" int ud_in_act_fwd(const float* x, const float* gamma, const float* be
 #undef IA_FWD
 #undef IA_FWD_V
   }
-  ia_fwd_generic_kernel<<<planes, IA_THREADS, 0, stream>>>(x, gamma, beta, y, mean, rstd, ymean, C, HW, eps, act);
+  ia_fwd_generic_kernel<IO><<<planes, IA_THREADS, 0, stream>>>(x, gamma, beta, y, mean, rstd, ymean, C, HW, eps, act);
   return ud_check_launch("ia_fwd_generic");
+}
+
+extern "C" int ud_in_act_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                             float* rstd, float* ymean, int N, int C, int HW, float eps, int act,
+                             cudaStream_t stream) {
+  return ia_fwd_impl<float>(x, gamma, beta, y, mean, rstd, ymean, N, C, HW, eps, act, stream);
+}
+extern "C" int ud_in_act_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                  float* rstd, float* ymean, int N, int C, int HW, float eps, int act,
+                                  cudaStream_t stream) {
+  return ia_fwd_impl<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean,
+                                    rstd, ymean, N, C, HW, eps, act, stream);
 }
 
 extern "C" size_t ud_in_act_bwd_workspace_bytes(int N, int C) { return sizeof(float) * 2ull * N * C; }
 
-extern "C" int ud_in_act_bwd(const float* x, const float* gy, const float* gamma, const float* beta,
-                             const float* mean, const float* rstd, const float* g_ymean, float* gx,
-                             float* ggamma, float* gbeta, void* ws, size_t ws_bytes, int N, int C, int HW, int act,
-                             cudaStream_t stream) {
+template <class IO>
+static int ia_bwd_impl(const IO* x, const IO* gy, const float* gamma, const float* beta, const float* mean,
+                       const float* rstd, const float* g_ymean, IO* gx, float* ggamma, float* gbeta, void* ws,
+                       size_t ws_bytes, int N, int C, int HW, int act, cudaStream_t stream) {
   UD_REQUIRE(N >= 0 && C >= 1 && HW >= 1, UD_ERR_INVALID, "in_act_bwd: bad shape N=%d C=%d HW=%d", N, C, HW);
   UD_REQUIRE(act >= UD_ACT_NONE && act <= UD_ACT_SWISH, UD_ERR_INVALID, "in_act_bwd: bad activation %d", act);
   if (N == 0) {
@@ -587,6 +613,8 @@ extern "C" int ud_in_act_bwd(const float* x, const float* gy, const float* gamma
   }
   UD_REQUIRE(x && gy && mean && rstd && gx && ws, UD_ERR_INVALID, "in_act_bwd: null pointer");
   UD_REQUIRE(ws_bytes >= ud_in_act_bwd_workspace_bytes(N, C), UD_ERR_WORKSPACE, "in_act_bwd: workspace too small");
+  typedef typename IaVec<IO>::V V;
+  constexpr int EPV = IaVec<IO>::E;
   float* s1 = static_cast<float*>(ws);
   float* s2 = s1 + (size_t)N * C;
   const int planes = N * C;
@@ -594,21 +622,22 @@ extern "C" int ud_in_act_bwd(const float* x, const float* gy, const float* gamma
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) |
                          reinterpret_cast<uintptr_t>(gx)) & 15) == 0;
   int G = 1;
-  if (aligned && ia_pick(HW, IA_VMAX_BWD, &G, &cs, &vpt)) {
-    const float4* x4 = reinterpret_cast<const float4*>(x);
-    const float4* g4 = reinterpret_cast<const float4*>(gy);
-    float4* o4 = reinterpret_cast<float4*>(gx);
+  if (aligned && ia_pick(HW, EPV, IaBudget<IO>::BWD, &G, &cs, &vpt)) {
+    const V* xv = reinterpret_cast<const V*>(x);
+    const V* gv = reinterpret_cast<const V*>(gy);
+    V* ov = reinterpret_cast<V*>(gx);
     rc = UD_OK;
     if (cs == 1)
-      IA_ACT_SWITCH(act, rc = ia_launch(ia_bwd_kernel<false, ACT_, IA_VMAX_BWD>, ud_cdiv(planes, IA_WARPS / G), 1, stream, x4,
-                                        g4, gamma, beta, mean, rstd, g_ymean, o4, s1, s2, planes, C, HW / 4, G, cs));
+      IA_ACT_SWITCH(act, rc = ia_launch(ia_bwd_kernel<IO, false, ACT_, IaBudget<IO>::BWD>, ud_cdiv(planes, IA_WARPS / G), 1,
+                                        stream, xv, gv, gamma, beta, mean, rstd, g_ymean, ov, s1, s2, planes, C, HW / EPV, G,
+                                        cs));
     else
-      IA_ACT_SWITCH(act, rc = ia_launch(ia_bwd_kernel<true, ACT_, IA_VMAX_BWD>, planes * cs, cs, stream, x4, g4, gamma, beta,
-                                        mean, rstd, g_ymean, o4, s1, s2, planes, C, HW / 4, G, cs));
+      IA_ACT_SWITCH(act, rc = ia_launch(ia_bwd_kernel<IO, true, ACT_, IaBudget<IO>::BWD>, planes * cs, cs, stream, xv, gv,
+                                        gamma, beta, mean, rstd, g_ymean, ov, s1, s2, planes, C, HW / EPV, G, cs));
     if (rc != UD_OK) return rc;
   } else {
-    ia_bwd_generic_kernel<<<planes, IA_THREADS, 0, stream>>>(x, gy, gamma, beta, mean, rstd, g_ymean, gx, s1, s2, C,
-                                                             HW, act);
+    ia_bwd_generic_kernel<IO><<<planes, IA_THREADS, 0, stream>>>(x, gy, gamma, beta, mean, rstd, g_ymean, gx, s1, s2, C, HW,
+                                                                  act);
     if ((rc = ud_check_launch("ia_bwd_generic")) != UD_OK) return rc;
   }
   if (ggamma || gbeta) {
@@ -616,6 +645,20 @@ extern "C" int ud_in_act_bwd(const float* x, const float* gy, const float* gamma
     return ud_check_launch("ia_param_grad");
   }
   return UD_OK;
+}
+
+extern "C" int ud_in_act_bwd(const float* x, const float* gy, const float* gamma, const float* beta,
+                             const float* mean, const float* rstd, const float* g_ymean, float* gx,
+                             float* ggamma, float* gbeta, void* ws, size_t ws_bytes, int N, int C, int HW, int act,
+                             cudaStream_t stream) {
+  return ia_bwd_impl<float>(x, gy, gamma, beta, mean, rstd, g_ymean, gx, ggamma, gbeta, ws, ws_bytes, N, C, HW, act, stream);
+}
+extern "C" int ud_in_act_bwd_bf16(const void* x, const void* gy, const float* gamma, const float* beta, const float* mean,
+                                  const float* rstd, const float* g_ymean, void* gx, float* ggamma, float* gbeta, void* ws,
+                                  size_t ws_bytes, int N, int C, int HW, int act, cudaStream_t stream) {
+  return ia_bwd_impl<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gy), gamma, beta,
+                                    mean, rstd, g_ymean, static_cast<__nv_bfloat16*>(gx), ggamma, gbeta, ws, ws_bytes, N, C,
+                                    HW, act, stream);
 }
 
 // ---- tanh epilogue (model/unidefense.py:101,:307,:499) ------------------------------------------

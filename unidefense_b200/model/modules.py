@@ -69,7 +69,9 @@ class DecoderBlock(nn.Sequential):
                     raise RuntimeError("DecoderBlock: InstanceNorm2d with running stats is not on the reference path")
                 act = act_name(mods[i + 1])
                 take = want_mean and i == last_norm and not any(isinstance(t, nn.Tanh) for t in mods)
-                r = ops.in_act(x.float(), m.weight, m.bias, act, m.eps, want_mean=take)
+                # bf16 in -> bf16 out under autocast (the convolutions on either side emit / consume bf16): no casting passes
+                xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+                r = ops.in_act(xin, m.weight, m.bias, act, m.eps, want_mean=take)
                 x, ymean = r if take else (r, ymean)
                 i += 2
             elif isinstance(m, nn.Tanh):

@@ -80,12 +80,14 @@ ACT_CODES = {"none": 0, "relu": 1, "swish": 2}
 
 
 class _InAct(torch.autograd.Function):
-    """a2: InstanceNorm2d(affine) + Swish/ReLU in one pass (model/unidefense.py:61-98 etc.)."""
+    """a2: InstanceNorm2d(affine) + Swish/ReLU in one pass (model/unidefense.py:61-98 etc.).  x may be fp32 or bf16
+    (the output, the saved input and the input gradient keep x's dtype; statistics, parameters and ymean are fp32)."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, act, eps, want_mean):
         x = x.contiguous()
-        L.require_cuda_f32(x, gamma, beta)
+        L.require_cuda_f32(x, also=(torch.bfloat16,))
+        L.require_cuda_f32(gamma, beta)
         N, C = x.shape[:2]
         HW = x[0, 0].numel() if N > 0 else int(torch.tensor(x.shape[2:]).prod())
         lib = L.lib()
@@ -93,8 +95,9 @@ class _InAct(torch.autograd.Function):
         mean = torch.empty(N * C, device=x.device, dtype=torch.float32)
         rstd = torch.empty(N * C, device=x.device, dtype=torch.float32)
         ymean = torch.empty(N, C, device=x.device, dtype=torch.float32) if want_mean else None
-        L.check(lib.ud_in_act_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ptr(mean), L.ptr(rstd),
-                                  L.ptr(ymean), N, C, HW, float(eps), act, L.stream()), "in_act_fwd")
+        fwd = lib.ud_in_act_fwd_bf16 if x.dtype == torch.bfloat16 else lib.ud_in_act_fwd
+        L.check(fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ptr(mean), L.ptr(rstd), L.ptr(ymean), N, C, HW,
+                    float(eps), act, L.stream()), "in_act_fwd")
         ctx.save_for_backward(x, gamma, beta, mean, rstd)
         ctx.act = act
         ctx.hw = HW
@@ -107,17 +110,17 @@ class _InAct(torch.autograd.Function):
         x, gamma, beta, mean, rstd = ctx.saved_tensors
         N, C = x.shape[:2]
         lib = L.lib()
-        gy = torch.zeros_like(x) if gy is None else gy.contiguous()
+        gy = torch.zeros_like(x) if gy is None else gy.to(x.dtype).contiguous()
         if g_ymean is not None:
-            g_ymean = g_ymean.contiguous()
+            g_ymean = g_ymean.float().contiguous()
         gx = torch.empty_like(x)
         ggamma = torch.empty_like(gamma) if gamma is not None else None
         gbeta = torch.empty_like(beta) if beta is not None else None
         nws = lib.ud_in_act_bwd_workspace_bytes(N, C)
         ws = L.workspace(nws, x.device)
-        L.check(lib.ud_in_act_bwd(L.ptr(x), L.ptr(gy), L.ptr(gamma), L.ptr(beta), L.ptr(mean), L.ptr(rstd),
-                                  L.ptr(g_ymean), L.ptr(gx), L.ptr(ggamma), L.ptr(gbeta), L.ptr(ws), ws.numel(),
-                                  N, C, ctx.hw, ctx.act, L.stream()), "in_act_bwd")
+        bwd = lib.ud_in_act_bwd_bf16 if x.dtype == torch.bfloat16 else lib.ud_in_act_bwd
+        L.check(bwd(L.ptr(x), L.ptr(gy), L.ptr(gamma), L.ptr(beta), L.ptr(mean), L.ptr(rstd), L.ptr(g_ymean), L.ptr(gx),
+                    L.ptr(ggamma), L.ptr(gbeta), L.ptr(ws), ws.numel(), N, C, ctx.hw, ctx.act, L.stream()), "in_act_bwd")
         return gx, ggamma, gbeta, None, None, None
 
 
