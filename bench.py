@@ -867,8 +867,18 @@ def run_ours(args):
         os._exit(0)
 
 
-# dram bytes per launch from the committed `ncu --set full` captures (profiles/), None until captured
-TRAFFIC = {}
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the launches of the group in one
+# step) from the committed ncu pass over the same kernels at the same shapes: profiles/r02_traffic.json, written by
+# tools/ncu_traffic.py.  None for a group that has not been captured.
+def _load_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return {k: v["dram_bytes_per_launch"] for k, v in json.load(f)["groups"].items()}
+    except (OSError, ValueError, KeyError):
+        return {}
+
+
+TRAFFIC = _load_traffic()
 
 
 def main():

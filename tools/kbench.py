@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", default="", help="in_act: restrict to one plane shape, e.g. 20x192")
     a = ap.parse_args()
     from unidefense_b200 import ops
     _, _, res, nb = bench.ARCH[a.arch]
@@ -84,6 +85,8 @@ def main():
         if tag not in want:
             continue
         for c, s in sorted(set(planes)):
+            if a.only and a.only != f"{c}x{s}":
+                continue
             x = torch.randn(nb, c, s, s, device=dev).to(io).requires_grad_()
             gamma = torch.rand(c, device=dev, requires_grad=True)
             beta = torch.randn(c, device=dev, requires_grad=True)

@@ -73,7 +73,9 @@ def _dft_mats(h, w, norm, device):
 
 def _dft_gemm_ok(x, spat):
     h, w = x.shape[-2:]
-    return (USE_DFT_GEMM and x.is_cuda and torch.is_autocast_enabled() and x.dim() == 4 and h <= _DFT_MAX and w <= _DFT_MAX
+    # bf16 autocast only: under fp16 autocast (or none) the transforms stay on the fp32 cuFFT path
+    return (USE_DFT_GEMM and x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+            and x.dim() == 4 and h <= _DFT_MAX and w <= _DFT_MAX
             and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
 
 
