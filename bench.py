@@ -833,7 +833,7 @@ def run_ours(args):
                              "peer_exchange_ms_per_step": round(comm_ms, 3),
                              "alg_mb_per_sample": mbs,
                              "hbm_frac_of_recon_path_kernels": (round(mbs * 1e6 * nb / (hot_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4)
-                                                                if mbs else None),
+                                                                if mbs and hot_ms > 0 else None),
                              "ops_ms_per_step": {k: round(v, 4) for k, v in sorted(ops_ms.items(), key=lambda kv: -kv[1])},
                              "ops_gbs": {k: round(v, 1) for k, v in timed.items()}}}
         if recon_ms is not None:

@@ -93,7 +93,7 @@ def test_sfconv_modules_reference_fixture(golden_ops, cl):
         assert m.sf_coef.grad is not None and m.weight.grad is not None
 
 
-@pytest.mark.parametrize("cfg", [(48, 24, 5, 2), (32, 12, 3, 1), (16, 48, 3, 1)])
+@pytest.mark.parametrize("cfg", [(48, 24, 5, 2), (32, 12, 3, 1), (16, 48, 3, 1), (24, 95, 5, 2), (8, 96, 3, 1)])
 def test_sfconv_paths_agree_bf16(cfg):
     """bf16 autocast + channels_last (the bench configuration): DFT-by-GEMM path and glue-kernel path vs the plain
     torch composition (bf16 tolerance: the twiddles themselves are bf16 in the GEMM path)."""
@@ -126,7 +126,7 @@ def test_sfconv_paths_agree_bf16(cfg):
 def test_dft_gemm_matrices_fp32():
     """The four DFT matrices reproduce rfft2+cat and tensor_split+complex+irfft2 exactly when run in fp32."""
     from unidefense_b200.model import sfconv
-    for (h, w) in [(12, 12), (24, 24), (48, 48), (9, 7), (8, 6)]:
+    for (h, w) in [(12, 12), (24, 24), (48, 48), (9, 7), (8, 6), (95, 95), (96, 64)]:
         for norm in ("ortho", None):
             N, C = 2, 6
             wh = w // 2 + 1

@@ -36,7 +36,9 @@ USE_GLUE_KERNELS = os.environ.get("UD_SFCONV_GLUE", "1") != "0"
 # Four batched library GEMMs replace copy->fp32, R2C, C2C, pack, unpack, C2R and their backward twins; autograd
 # differentiates the matmuls.  Exact fp32 runs keep the cuFFT path (bf16 twiddles carry ~3 significant digits).
 USE_DFT_GEMM = os.environ.get("UD_SFCONV_DFT_GEMM", "1") != "0"
-_DFT_MAX = 64
+# largest side evaluated as DFT-by-GEMM: 96 covers every SFConv layer of the shipped configs (95^2 at EB4@380 is the
+# biggest: with it on the GEMM path the step went 77.2 -> 74.0 ms on a B200; 64 was the round-1 setting)
+_DFT_MAX = int(os.environ.get("UD_SFCONV_DFT_MAX", "96"))
 _dft_cache = {}
 
 
@@ -74,7 +76,7 @@ def _dft_mats(h, w, norm, device):
 def _dft_gemm_ok(x, spat):
     h, w = x.shape[-2:]
     # bf16 autocast only: under fp16 autocast (or none) the transforms stay on the fp32 cuFFT path
-    return (USE_DFT_GEMM and x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+    return (USE_DFT_GEMM and x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
             and x.dim() == 4 and h <= _DFT_MAX and w <= _DFT_MAX
             and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
 
