@@ -142,3 +142,18 @@ def test_attn_fuse(shape, with_res):
             assert ts[i].grad is None
             continue
         close(ts[i].grad, t64[i].grad, rtol=2e-4, atol=1e-5 * float(t64[i].grad.abs().max()) + 1e-7)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 380, 380), (2, 3, 224, 224), (1, 2, 62, 80), (3, 3, 24, 24)])
+def test_spectral_mask_filter_composite(shape):
+    """The C5 composite irfft2(mask * rfft2(x)) (generic transforms, mask folded into the inverse's load) vs torch.fft."""
+    from unidefense_b200 import ops
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.randn(shape, generator=g)
+    mask = torch.rand(N, H, W // 2 + 1, generator=g)
+    y = ops.spectral_mask_filter(x.cuda(), mask.cuda())
+    want = torch.fft.irfft2(torch.fft.rfft2(x.double(), norm="ortho") * mask.double().unsqueeze(1), s=(H, W), norm="ortho")
+    close(y, want)
+    with pytest.raises(ValueError):
+        ops.spectral_mask_filter(x.cuda(), mask[:, :-1].cuda())

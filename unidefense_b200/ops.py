@@ -261,6 +261,21 @@ def irfft2_cat(xf, size, norm="ortho"):
     return _Irfft2Cat.apply(xf, int(size[0]), int(size[1]), norm_flag(norm))
 
 
+def spectral_mask_filter(x, mask, norm="ortho"):
+    """y = irfft2(mask * rfft2(x)) for any plane size (no grad): the composite of BASELINE.json's frequency-branch
+    microbench (configs[4]: batched FFT2 + mask + IFFT2).  x [N,C,H,W]; mask [N,H,W/2+1] is shared by the channels of a
+    sample, as the dynamic filter's mask is (model/unidefense.py:140-145).  Two generic transforms (csrc/ud_fft2d.cu);
+    the mask multiply rides on the inverse transform's load."""
+    x = x.detach().contiguous()
+    mask = mask.detach().contiguous()
+    L.require_cuda_f32(x, mask)
+    N, C, H, W = x.shape
+    if tuple(mask.shape) != (N, H, W // 2 + 1):
+        raise ValueError(f"spectral_mask_filter: mask {tuple(mask.shape)} does not match [N,H,W/2+1] of {tuple(x.shape)}")
+    nf = norm_flag(norm)
+    return _irfft2_raw(_rfft2_raw(x, nf, 0), mask, H, W, nf, 0)
+
+
 class _AttnFuse(torch.autograd.Function):
     """out = (1-s)*smask*emb + s*ff + res, s = sigmoid(fuse_coef) (model/unidefense.py:153-155).
     res=None means the residual is emb itself (dropout inactive)."""
