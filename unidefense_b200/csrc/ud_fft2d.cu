@@ -27,6 +27,17 @@ int ud_irfft2_small(const float* xf, const float* mask, float* y, int N, int C, 
                     int adjoint_of_forward, cudaStream_t stream);
 bool ud_fft2_small_ok(int h, int w);
 
+static bool f2_static(int n) { return n == 380 || n == 256 || n == 224 || n == 299; }
+// runs the body with PL bound to the static in-place plan of n (L = F2_L lines) or to the run-time plan `any`
+#define F2_DISPATCH(n, any, PL, Lvar, ...)                                                                       \
+  do {                                                                                                           \
+    if ((n) == 380) { UdStaticPlanIP<380, F2_L, F2_THREADS, 19, 5, 4> PL; const int Lvar = F2_L; __VA_ARGS__; }   \
+    else if ((n) == 256) { UdStaticPlanIP<256, F2_L, F2_THREADS, 4, 4, 4, 4> PL; const int Lvar = F2_L; __VA_ARGS__; } \
+    else if ((n) == 224) { UdStaticPlanIP<224, F2_L, F2_THREADS, 7, 4, 4, 2> PL; const int Lvar = F2_L; __VA_ARGS__; } \
+    else if ((n) == 299) { UdStaticPlanIP<299, F2_L, F2_THREADS, 23, 13> PL; const int Lvar = F2_L; __VA_ARGS__; } \
+    else { UdAnyPlan PL = (any); const int Lvar = f2_lines(any); __VA_ARGS__; }                                  \
+  } while (0)
+
 static int f2_lines(const UdAnyPlan& p) {
   const size_t per = 2ull * (size_t)ud_any_line_stride(p) * sizeof(float2);
   int L = (int)((96u << 10) / per);
@@ -37,24 +48,32 @@ static int f2_lines(const UdAnyPlan& p) {
 static size_t f2_smem(const UdAnyPlan& p, int L) {
   return sizeof(float2) * ((size_t)p.m + 2ull * L * ud_any_line_stride(p));
 }
+static size_t f2_smem_n(int n, const UdAnyPlan& p, int L) {      // static plans: m = n, same two-buffer layout
+  return f2_static(n) ? sizeof(float2) * ((size_t)n + 2ull * L * (size_t)(n | 1)) : f2_smem(p, L);
+}
 
-__device__ __forceinline__ void f2_stage_tw(float2* tw_s, const UdAnyPlan& p) {
-  for (int t = threadIdx.x; t < p.m; t += blockDim.x) tw_s[t] = __ldg(p.tw + t);
+// Plans: UdAnyPlan (any size, run time) or the in-place static plans of the configured image sizes (every index
+// constant-folded; F2_L lines per CTA, F2_THREADS threads).  `tw_g` = exp(-2 pi i t / m), t < m = plan.line_len().
+#define F2_L 16
+template <class Plan>
+__device__ __forceinline__ void f2_stage_tw(float2* tw_s, const Plan& p, const float2* __restrict__ tw_g) {
+  for (int t = threadIdx.x; t < p.line_len(); t += blockDim.x) tw_s[t] = __ldg(tw_g + t);
 }
 
 // rows of the forward transform: line l = rows (2p, 2p+1) of the plane packed as a + i b
+template <class Plan>
 __global__ void __launch_bounds__(F2_THREADS)
-f2_rows_r2c_kernel(UdAnyPlan plan, const float* __restrict__ x, float2* __restrict__ T, int h, int w, int L,
+f2_rows_r2c_kernel(Plan plan, const float2* __restrict__ tw_g, const float* __restrict__ x, float2* __restrict__ T, int h, int w, int L,
                    int plane0) {
   extern __shared__ float2 f2sm[];
-  const int LS = plan.m | 1, wh = w / 2 + 1;
+  const int LS = plan.line_len() | 1, wh = w / 2 + 1;
   float2* tw_s = f2sm;
-  float2* a = tw_s + plan.m;
+  float2* a = tw_s + plan.line_len();
   float2* b = a + L * LS;
   const long long plane = (long long)plane0 + blockIdx.y;
   const int p0 = blockIdx.x * L;                      // first row pair of this CTA
   const float* xp = x + plane * (long long)h * w;
-  f2_stage_tw(tw_s, plan);
+  f2_stage_tw(tw_s, plan, tw_g);
   for (int idx = threadIdx.x; idx < L * w; idx += blockDim.x) {
     const int l = idx / w, j = idx - l * w;
     const int r = 2 * (p0 + l);
@@ -76,18 +95,19 @@ f2_rows_r2c_kernel(UdAnyPlan plan, const float* __restrict__ x, float2* __restri
 }
 
 // columns of the forward transform: line l = column k0 + l of T; planar store with scale and column multipliers
+template <class Plan>
 __global__ void __launch_bounds__(F2_THREADS)
-f2_cols_fwd_kernel(UdAnyPlan plan, const float2* __restrict__ T, float* __restrict__ out, int C, int h, int w, int L,
+f2_cols_fwd_kernel(Plan plan, const float2* __restrict__ tw_g, const float2* __restrict__ T, float* __restrict__ out, int C, int h, int w, int L,
                    float scale, int colmul, int plane0) {
   extern __shared__ float2 f2sm[];
-  const int LS = plan.m | 1, wh = w / 2 + 1;
+  const int LS = plan.line_len() | 1, wh = w / 2 + 1;
   float2* tw_s = f2sm;
-  float2* a = tw_s + plan.m;
+  float2* a = tw_s + plan.line_len();
   float2* b = a + L * LS;
   const long long plane = (long long)plane0 + blockIdx.y;
   const int k0 = blockIdx.x * L;
   const float2* Tp = T + plane * (long long)h * wh;
-  f2_stage_tw(tw_s, plan);
+  f2_stage_tw(tw_s, plan, tw_g);
   for (int idx = threadIdx.x; idx < L * h; idx += blockDim.x) {
     const int r = idx / L, l = idx - r * L;
     a[l * LS + r] = (k0 + l < wh) ? __ldg(Tp + (long long)r * wh + k0 + l) : make_float2(0.f, 0.f);
@@ -110,13 +130,14 @@ f2_cols_fwd_kernel(UdAnyPlan plan, const float2* __restrict__ T, float* __restri
 }
 
 // columns of the inverse transform: U[r][k] = sum_j m_k Z[j][k] e^{+2 pi i j r / h}  (unnormalised)
+template <class Plan>
 __global__ void __launch_bounds__(F2_THREADS)
-f2_cols_inv_kernel(UdAnyPlan plan, const float* __restrict__ in, const float* __restrict__ mask, float2* __restrict__ T,
+f2_cols_inv_kernel(Plan plan, const float2* __restrict__ tw_g, const float* __restrict__ in, const float* __restrict__ mask, float2* __restrict__ T,
                    int C, int h, int w, int L, int colmul, int plane0) {
   extern __shared__ float2 f2sm[];
-  const int LS = plan.m | 1, wh = w / 2 + 1;
+  const int LS = plan.line_len() | 1, wh = w / 2 + 1;
   float2* tw_s = f2sm;
-  float2* a = tw_s + plan.m;
+  float2* a = tw_s + plan.line_len();
   float2* b = a + L * LS;
   const long long plane = (long long)plane0 + blockIdx.y;
   const int k0 = blockIdx.x * L;
@@ -125,7 +146,7 @@ f2_cols_inv_kernel(UdAnyPlan plan, const float* __restrict__ in, const float* __
   const float* iim = in + (n * 2 * C + C + c) * (long long)h * wh;
   const float* mk = mask ? mask + n * (long long)h * wh : nullptr;
   const int last = (w % 2 == 0) ? wh - 1 : wh;
-  f2_stage_tw(tw_s, plan);
+  f2_stage_tw(tw_s, plan, tw_g);
   for (int idx = threadIdx.x; idx < L * h; idx += blockDim.x) {
     const int r = idx / L, l = idx - r * L;
     const int k = k0 + l;
@@ -150,18 +171,19 @@ f2_cols_inv_kernel(UdAnyPlan plan, const float* __restrict__ in, const float* __
 }
 
 // rows of the inverse transform: y[r][c] = scale * Re sum_{k < wh} U[r][k] e^{+2 pi i k c / w}
+template <class Plan>
 __global__ void __launch_bounds__(F2_THREADS)
-f2_rows_c2r_kernel(UdAnyPlan plan, const float2* __restrict__ T, float* __restrict__ y, int h, int w, int L, float scale,
+f2_rows_c2r_kernel(Plan plan, const float2* __restrict__ tw_g, const float2* __restrict__ T, float* __restrict__ y, int h, int w, int L, float scale,
                    int plane0) {
   extern __shared__ float2 f2sm[];
-  const int LS = plan.m | 1, wh = w / 2 + 1;
+  const int LS = plan.line_len() | 1, wh = w / 2 + 1;
   float2* tw_s = f2sm;
-  float2* a = tw_s + plan.m;
+  float2* a = tw_s + plan.line_len();
   float2* b = a + L * LS;
   const long long plane = (long long)plane0 + blockIdx.y;
   const int r0 = blockIdx.x * L;
   const float2* Tp = T + plane * (long long)h * wh;
-  f2_stage_tw(tw_s, plan);
+  f2_stage_tw(tw_s, plan, tw_g);
   for (int idx = threadIdx.x; idx < L * w; idx += blockDim.x) {
     const int l = idx / w, k = idx - l * w;
     float2 v = make_float2(0.f, 0.f);
@@ -217,15 +239,22 @@ extern "C" int ud_rfft2(const float* x, float* xf, void* ws, size_t ws_bytes, in
   if (!ud_make_any_plan(w, &pw) || !ud_make_any_plan(h, &ph)) return UD_ERR_UNSUPPORTED;
   float2* T = static_cast<float2*>(ws);
   const int planes = N * C, wh = w / 2 + 1;
-  const int Lw = f2_lines(pw), Lh = f2_lines(ph);
-  if ((rc = f2_set_smem(f2_rows_r2c_kernel, f2_smem(pw, Lw))) != UD_OK) return rc;
-  if ((rc = f2_set_smem(f2_cols_fwd_kernel, f2_smem(ph, Lh))) != UD_OK) return rc;
+  const float scale = f2_scale(h, w, norm_ortho, adjoint_of_inverse != 0);
   for (int p0 = 0; p0 < planes; p0 += F2_MAX_GRID_Y) {            // gridDim.y <= 65535
     const int np = planes - p0 < F2_MAX_GRID_Y ? planes - p0 : F2_MAX_GRID_Y;
-    f2_rows_r2c_kernel<<<dim3(ud_cdiv((h + 1) / 2, Lw), np), F2_THREADS, f2_smem(pw, Lw), stream>>>(pw, x, T, h, w, Lw, p0);
+    F2_DISPATCH(w, pw, pl, L, {
+      auto k = f2_rows_r2c_kernel<decltype(pl)>;
+      const size_t sm = f2_smem_n(w, pw, L);
+      if ((rc = f2_set_smem(k, sm)) != UD_OK) return rc;
+      k<<<dim3(ud_cdiv((h + 1) / 2, L), np), F2_THREADS, sm, stream>>>(pl, pw.tw, x, T, h, w, L, p0);
+    });
     if ((rc = ud_check_launch("rfft2_rows")) != UD_OK) return rc;
-    f2_cols_fwd_kernel<<<dim3(ud_cdiv(wh, Lh), np), F2_THREADS, f2_smem(ph, Lh), stream>>>(
-        ph, T, xf, C, h, w, Lh, f2_scale(h, w, norm_ortho, adjoint_of_inverse != 0), adjoint_of_inverse, p0);
+    F2_DISPATCH(h, ph, pl, L, {
+      auto k = f2_cols_fwd_kernel<decltype(pl)>;
+      const size_t sm = f2_smem_n(h, ph, L);
+      if ((rc = f2_set_smem(k, sm)) != UD_OK) return rc;
+      k<<<dim3(ud_cdiv(wh, L), np), F2_THREADS, sm, stream>>>(pl, ph.tw, T, xf, C, h, w, L, scale, adjoint_of_inverse, p0);
+    });
     if ((rc = ud_check_launch("rfft2_cols")) != UD_OK) return rc;
   }
   return UD_OK;
@@ -243,16 +272,22 @@ extern "C" int ud_irfft2(const float* xf, const float* mask, float* y, void* ws,
   if (!ud_make_any_plan(w, &pw) || !ud_make_any_plan(h, &ph)) return UD_ERR_UNSUPPORTED;
   float2* T = static_cast<float2*>(ws);
   const int planes = N * C, wh = w / 2 + 1;
-  const int Lw = f2_lines(pw), Lh = f2_lines(ph);
-  if ((rc = f2_set_smem(f2_cols_inv_kernel, f2_smem(ph, Lh))) != UD_OK) return rc;
-  if ((rc = f2_set_smem(f2_rows_c2r_kernel, f2_smem(pw, Lw))) != UD_OK) return rc;
+  const float scale = f2_scale(h, w, norm_ortho, adjoint_of_forward == 0);
   for (int p0 = 0; p0 < planes; p0 += F2_MAX_GRID_Y) {
     const int np = planes - p0 < F2_MAX_GRID_Y ? planes - p0 : F2_MAX_GRID_Y;
-    f2_cols_inv_kernel<<<dim3(ud_cdiv(wh, Lh), np), F2_THREADS, f2_smem(ph, Lh), stream>>>(ph, xf, mask, T, C, h, w, Lh,
-                                                                                          adjoint_of_forward ? 0 : 1, p0);
+    F2_DISPATCH(h, ph, pl, L, {
+      auto k = f2_cols_inv_kernel<decltype(pl)>;
+      const size_t sm = f2_smem_n(h, ph, L);
+      if ((rc = f2_set_smem(k, sm)) != UD_OK) return rc;
+      k<<<dim3(ud_cdiv(wh, L), np), F2_THREADS, sm, stream>>>(pl, ph.tw, xf, mask, T, C, h, w, L, adjoint_of_forward ? 0 : 1, p0);
+    });
     if ((rc = ud_check_launch("irfft2_cols")) != UD_OK) return rc;
-    f2_rows_c2r_kernel<<<dim3(ud_cdiv(h, Lw), np), F2_THREADS, f2_smem(pw, Lw), stream>>>(
-        pw, T, y, h, w, Lw, f2_scale(h, w, norm_ortho, adjoint_of_forward == 0), p0);
+    F2_DISPATCH(w, pw, pl, L, {
+      auto k = f2_rows_c2r_kernel<decltype(pl)>;
+      const size_t sm = f2_smem_n(w, pw, L);
+      if ((rc = f2_set_smem(k, sm)) != UD_OK) return rc;
+      k<<<dim3(ud_cdiv(h, L), np), F2_THREADS, sm, stream>>>(pl, pw.tw, T, y, h, w, L, scale, p0);
+    });
     if ((rc = ud_check_launch("irfft2_rows")) != UD_OK) return rc;
   }
   return UD_OK;
