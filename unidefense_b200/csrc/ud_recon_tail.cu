@@ -31,7 +31,19 @@ int ud_rt2_fwd(const float* dec, const float* x, float* rec, float2* Z, float* p
 int ud_rt2_bwd(const float* dec, const float* x, const uint8_t* signs, const float* g_spatial, const float* g_freq,
                float* g_dec, float2* T, int plane0, int planes, int C, int h, int w, int H, int W, int row_tiles,
                int col_tiles, float gscale, float sp_scale, cudaStream_t stream);
-#define RT2_PAIRS_PER_TILE 32   // RT2_LPC * RT2_ITER of ud_recon_tail2.cu
+// row pairs per rows-CTA of ud_recon_tail2.cu = its RT2_LPC (16) x the steps a CTA walks.  Measured at N=32, 380^2: one
+// step per CTA (12 row tiles per plane, ~4 waves) and two (6 tiles, ~2 waves) take the same time (101 / 89 us fwd / bwd),
+// three is 10-30 % slower: the kernels are bound per SM (issue + L2 latency at 20 resident warps), not by wave shape.
+// UD_RT2_ITER overrides (profiling aid).
+static int rt2_pairs_per_tile() {
+  static const int iters = [] {
+    const char* e = getenv("UD_RT2_ITER");
+    const int v = e ? atoi(e) : 1;
+    return v >= 1 && v <= 8 ? v : 1;
+  }();
+  return 16 * iters;
+}
+#define RT2_PAIRS_PER_TILE rt2_pairs_per_tile()
 #define RT2_COLS_PER_TILE 16
 static bool rt_use_v2(int h, int w, int H, int W) {
   static const bool force_v1 = getenv("UD_RT_V1") != nullptr;      // A/B switch for profiling

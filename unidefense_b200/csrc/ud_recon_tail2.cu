@@ -21,7 +21,7 @@
 #include "ud_fft2s.cuh"
 
 #define RT2_LPC 16    // lines (row pairs / columns) per CTA step
-#define RT2_ITER 2    // row-pair steps per CTA of the rows kernels
+// row-pair steps per CTA of the rows kernels: a launch parameter (`iters`, derived from the row-tile count the caller chose)
 
 __device__ __forceinline__ void rt2_tab(const float2 t, int in_size, int& i0, int& i1, float& l0, float& l1) {
   i0 = __float_as_int(t.x);
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(PL::TL* RT2_LPC, 2)
 rt2_rows_fwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, float* __restrict__ rec,
                     float2* __restrict__ Z, float* __restrict__ part_spatial, const float2* __restrict__ tw_g,
                     const float2* __restrict__ ytab_g, const float2* __restrict__ xtab_g, int plane0, int h, int w, int H,
-                    int row_tiles) {
+                    int row_tiles, int iters) {
   constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, TL = PL::TL, P = PL::P, LS = PL::LS;
   extern __shared__ float2 smem[];
   float2* tw2 = smem;
@@ -76,7 +76,7 @@ rt2_rows_fwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
   const int pl = blockIdx.y;
   const long long plane = plane0 + pl;
   const int Hp = (H + 1) >> 1;
-  const int pair0 = blockIdx.x * (RT2_LPC * RT2_ITER);
+  const int pair0 = blockIdx.x * (RT2_LPC * iters);
 
   ud2s_build_tw<PL>(tw2, tw_g);
   for (int t = tid; t < N; t += TL * RT2_LPC) xtab[t] = __ldg(xtab_g + t);
@@ -86,7 +86,7 @@ rt2_rows_fwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
   float2* Zp = Z + (long long)pl * Hp * N;
   float acc = 0.f;
 #pragma unroll 1
-  for (int it = 0; it < RT2_ITER; ++it) {
+  for (int it = 0; it < iters; ++it) {
     const int pbase = pair0 + it * RT2_LPC;
     if (pbase >= Hp) break;
     const int p = pbase + g, ra = 2 * p;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(PL::TL* RT2_LPC, 2)
 rt2_rows_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, const float2* __restrict__ T,
                     const float* __restrict__ g_spatial, const float* __restrict__ g_freq, float* __restrict__ g_dec,
                     const float2* __restrict__ tw_g, const float2* __restrict__ ytab_g, const float2* __restrict__ xtab_g,
-                    const int2* __restrict__ jtab_g, int plane0, int C, int h, int w, int H, float sp_scale) {
+                    const int2* __restrict__ jtab_g, int plane0, int C, int h, int w, int H, float sp_scale, int iters) {
   constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, TL = PL::TL, P = PL::P, LS = PL::LS;
   constexpr int NT = TL * RT2_LPC;
   extern __shared__ float2 smem[];
@@ -325,7 +325,7 @@ rt2_rows_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
   const int Hp = (H + 1) >> 1;
   const int Wh = N / 2 + 1;
   const int WhP = (Wh + 15) & ~15;
-  const int pair0 = blockIdx.x * (RT2_LPC * RT2_ITER);
+  const int pair0 = blockIdx.x * (RT2_LPC * iters);
 
   ud2s_build_tw<PL>(tw2, tw_g);
   for (int t = tid; t < N; t += NT) xtab[t] = __ldg(xtab_g + t);
@@ -338,7 +338,7 @@ rt2_rows_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
   float acc0 = 0.f, acc1 = 0.f;
   if (tid < w && 2 * pair0 < H) cur = __float_as_int(__ldg(ytab_g + 2 * pair0).x);
 #pragma unroll 1
-  for (int it = 0; it < RT2_ITER; ++it) {
+  for (int it = 0; it < iters; ++it) {
     const int pbase = pair0 + it * RT2_LPC;
     if (pbase >= Hp) break;
     const int p = pbase + g, ra = 2 * p;
@@ -457,6 +457,9 @@ rt2_rows_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
     else { typedef Ud2S<299, 13, 23> PLV; __VA_ARGS__; }                   \
   } while (0)
 
+// steps of RT2_LPC row pairs a rows CTA walks so that `row_tiles` CTAs cover the (H+1)/2 pairs of a plane
+static int rt2_iters(int H, int row_tiles) { return ud_cdiv(ud_cdiv((H + 1) / 2, RT2_LPC), row_tiles); }
+
 static bool rt2_size(int n) { return n == 380 || n == 256 || n == 224 || n == 299; }
 
 // decoder planes at most as wide as the widest thread block (the vertical walk uses one thread per dec column)
@@ -494,7 +497,7 @@ int ud_rt2_fwd(const float* dec, const float* x, float* rec, float2* Z, float* p
     const size_t sm = sizeof(float2) * ((size_t)PLW::R1 * PLW::P + W + (size_t)RT2_LPC * PLW::LS + (size_t)RT2_LPC * w);
     if ((rc = rt2_set_smem(k, sm)) != UD_OK) return rc;
     k<<<dim3(row_tiles, planes), PLW::TL * RT2_LPC, sm, stream>>>(dec, x, rec, Z, part_sp, twW, ytab, xtab, plane0, h, w, H,
-                                                                    row_tiles);
+                                                                    row_tiles, rt2_iters(H, row_tiles));
   });
   if ((rc = ud_check_launch("rt2_rows_fwd")) != UD_OK) return rc;
   RT2_DISPATCH(H, PLH, {
@@ -531,7 +534,7 @@ int ud_rt2_bwd(const float* dec, const float* x, const uint8_t* signs, const flo
     const size_t sm = sizeof(float2) * ((size_t)PLW::R1 * PLW::P + W + (size_t)RT2_LPC * PLW::LS + (size_t)RT2_LPC * w);
     if ((rc = rt2_set_smem(k, sm)) != UD_OK) return rc;
     k<<<dim3(row_tiles, planes), PLW::TL * RT2_LPC, sm, stream>>>(dec, x, T, g_spatial, g_freq, g_dec, twW, ytab, xtab,
-                                                                    jtab, plane0, C, h, w, H, sp_scale);
+                                                                    jtab, plane0, C, h, w, H, sp_scale, rt2_iters(H, row_tiles));
   });
   return ud_check_launch("rt2_rows_bwd");
 }
