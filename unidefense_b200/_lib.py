@@ -11,7 +11,7 @@ import types
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libunidefense_b200.so")
+LIB_PATH = os.environ.get("UD_LIB_PATH") or os.path.join(_HERE, "libunidefense_b200.so")     # (override: A/B builds)
 _lib = None
 _lock = threading.Lock()
 

@@ -25,6 +25,7 @@
 
 // second-generation kernels for the configured image sizes (ud_recon_tail2.cu)
 bool ud_rt2_supported(int h, int w, int H, int W);
+int ud_rt2_rows_lpc(void);
 size_t ud_rt2_workspace_plane_bytes(int H, int W);
 int ud_rt2_fwd(const float* dec, const float* x, float* rec, float2* Z, float* part_sp, float* part_fr, uint8_t* signs,
                int plane0, int planes, int h, int w, int H, int W, int row_tiles, int col_tiles, cudaStream_t stream);
@@ -41,7 +42,7 @@ static int rt2_pairs_per_tile() {
     const int v = e ? atoi(e) : 1;
     return v >= 1 && v <= 8 ? v : 1;
   }();
-  return 16 * iters;
+  return ud_rt2_rows_lpc() * iters;
 }
 #define RT2_PAIRS_PER_TILE rt2_pairs_per_tile()
 #define RT2_COLS_PER_TILE 16

@@ -20,7 +20,13 @@
 #include "ud_fft.cuh"
 #include "ud_fft2s.cuh"
 
-#define RT2_LPC 16    // lines (row pairs / columns) per CTA step
+#define RT2_LPC 16    // columns per CTA step of the cols kernels (16 float2 = one 128-byte line per row)
+#ifndef RT2_RLPC
+// row pairs per CTA step of the rows kernels (threads = TL * RT2_RLPC).  Measured at N=32, 380^2 (fwd / bwd us): 16 ->
+// 101 / 89 (96 registers, 376 B spilled in rows_bwd, 20 warps per SM); 12 -> 110 / 95 and 10 -> 112 / 105 (128 registers,
+// fewer spills, 15 warps per SM): resident warps matter more than the spills.
+#define RT2_RLPC 16
+#endif
 // row-pair steps per CTA of the rows kernels: a launch parameter (`iters`, derived from the row-tile count the caller chose)
 
 __device__ __forceinline__ void rt2_tab(const float2 t, int in_size, int& i0, int& i1, float& l0, float& l1) {
@@ -56,11 +62,11 @@ __device__ __forceinline__ void rt2_vrows(const float* __restrict__ decp, const 
 }
 
 // ------------------------------------------------------------------------------------------
-// forward rows: grid (row_tiles, planes_in_chunk), PL::TL * RT2_LPC threads
+// forward rows: grid (row_tiles, planes_in_chunk), PL::TL * RT2_RLPC threads
 //   shared: tw2[R1*P] | xtab[N] | S[LPC*LS] | V[LPC*w]
 // ------------------------------------------------------------------------------------------
 template <class PL>
-__global__ void __launch_bounds__(PL::TL* RT2_LPC, 2)
+__global__ void __launch_bounds__(PL::TL* RT2_RLPC, 2)
 rt2_rows_fwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, float* __restrict__ rec,
                     float2* __restrict__ Z, float* __restrict__ part_spatial, const float2* __restrict__ tw_g,
                     const float2* __restrict__ ytab_g, const float2* __restrict__ xtab_g, int plane0, int h, int w, int H,
@@ -70,16 +76,16 @@ rt2_rows_fwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
   float2* tw2 = smem;
   float2* xtab = tw2 + R1 * P;
   float2* S = xtab + N;
-  float2* V = S + RT2_LPC * LS;
+  float2* V = S + RT2_RLPC * LS;
   __shared__ float red[33];
   const int tid = threadIdx.x, g = tid / TL, ln = tid - g * TL;
   const int pl = blockIdx.y;
   const long long plane = plane0 + pl;
   const int Hp = (H + 1) >> 1;
-  const int pair0 = blockIdx.x * (RT2_LPC * iters);
+  const int pair0 = blockIdx.x * (RT2_RLPC * iters);
 
   ud2s_build_tw<PL>(tw2, tw_g);
-  for (int t = tid; t < N; t += TL * RT2_LPC) xtab[t] = __ldg(xtab_g + t);
+  for (int t = tid; t < N; t += TL * RT2_RLPC) xtab[t] = __ldg(xtab_g + t);
   const float* decp = dec + plane * (long long)h * w;
   const float* xp = x + plane * (long long)H * N;
   float* recp = rec + plane * (long long)H * N;
@@ -87,7 +93,7 @@ rt2_rows_fwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
   float acc = 0.f;
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
-    const int pbase = pair0 + it * RT2_LPC;
+    const int pbase = pair0 + it * RT2_RLPC;
     if (pbase >= Hp) break;
     const int p = pbase + g, ra = 2 * p;
     const bool live = ra < H, has_b = ra + 1 < H;
@@ -302,18 +308,18 @@ rt2_cols_bwd_kernel(const uint8_t* __restrict__ signs, const float* __restrict__
 //   shared: tw2[R1*P] | xtab[N] | S[LPC*LS] | V[LPC*w] (aliased by Hb[2*LPC][w] floats)
 // ------------------------------------------------------------------------------------------
 template <class PL>
-__global__ void __launch_bounds__(PL::TL* RT2_LPC, 2)
+__global__ void __launch_bounds__(PL::TL* RT2_RLPC, 2)
 rt2_rows_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, const float2* __restrict__ T,
                     const float* __restrict__ g_spatial, const float* __restrict__ g_freq, float* __restrict__ g_dec,
                     const float2* __restrict__ tw_g, const float2* __restrict__ ytab_g, const float2* __restrict__ xtab_g,
                     const int2* __restrict__ jtab_g, int plane0, int C, int h, int w, int H, float sp_scale, int iters) {
   constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, TL = PL::TL, P = PL::P, LS = PL::LS;
-  constexpr int NT = TL * RT2_LPC;
+  constexpr int NT = TL * RT2_RLPC;
   extern __shared__ float2 smem[];
   float2* tw2 = smem;
   float2* xtab = tw2 + R1 * P;
   float2* S = xtab + N;
-  float2* V = S + RT2_LPC * LS;
+  float2* V = S + RT2_RLPC * LS;
   float* Hb = reinterpret_cast<float*>(V);            // [2*LPC][w] floats == LPC*w float2
   const int tid = threadIdx.x, g = tid / TL, ln = tid - g * TL;
   const int pl = blockIdx.y;
@@ -325,7 +331,7 @@ rt2_rows_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
   const int Hp = (H + 1) >> 1;
   const int Wh = N / 2 + 1;
   const int WhP = (Wh + 15) & ~15;
-  const int pair0 = blockIdx.x * (RT2_LPC * iters);
+  const int pair0 = blockIdx.x * (RT2_RLPC * iters);
 
   ud2s_build_tw<PL>(tw2, tw_g);
   for (int t = tid; t < N; t += NT) xtab[t] = __ldg(xtab_g + t);
@@ -339,7 +345,7 @@ rt2_rows_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
   if (tid < w && 2 * pair0 < H) cur = __float_as_int(__ldg(ytab_g + 2 * pair0).x);
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
-    const int pbase = pair0 + it * RT2_LPC;
+    const int pbase = pair0 + it * RT2_RLPC;
     if (pbase >= Hp) break;
     const int p = pbase + g, ra = 2 * p;
     const bool live = ra < H, has_b = ra + 1 < H;
@@ -401,7 +407,7 @@ rt2_rows_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
     }
     __syncthreads();
     // horizontal transposed lerp: Hb[2*gg + {0,1}][j] for every dec column j of every line
-    for (int idx = tid; idx < RT2_LPC * w; idx += NT) {
+    for (int idx = tid; idx < RT2_RLPC * w; idx += NT) {
       const int gg = idx / w, j = idx - gg * w;
       const int2 cr = __ldg(jtab_g + j);
       const float2* Gg = S + gg * LS;
@@ -421,7 +427,7 @@ rt2_rows_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
     // vertical transposed lerp: thread j walks the rows of this step in order, two running sums
     if (tid < w) {
       const int r0 = 2 * pbase;
-      const int nrows = min(2 * RT2_LPC, H - r0);
+      const int nrows = min(2 * RT2_RLPC, H - r0);
       for (int rr = 0; rr < nrows; ++rr) {
         int i0, i1;
         float l0, l1;
@@ -457,8 +463,9 @@ rt2_rows_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ x, 
     else { typedef Ud2S<299, 13, 23> PLV; __VA_ARGS__; }                   \
   } while (0)
 
-// steps of RT2_LPC row pairs a rows CTA walks so that `row_tiles` CTAs cover the (H+1)/2 pairs of a plane
-static int rt2_iters(int H, int row_tiles) { return ud_cdiv(ud_cdiv((H + 1) / 2, RT2_LPC), row_tiles); }
+// steps of RT2_RLPC row pairs a rows CTA walks so that `row_tiles` CTAs cover the (H+1)/2 pairs of a plane
+int ud_rt2_rows_lpc(void) { return RT2_RLPC; }
+static int rt2_iters(int H, int row_tiles) { return ud_cdiv(ud_cdiv((H + 1) / 2, RT2_RLPC), row_tiles); }
 
 static bool rt2_size(int n) { return n == 380 || n == 256 || n == 224 || n == 299; }
 
@@ -468,7 +475,7 @@ bool ud_rt2_supported(int h, int w, int H, int W) {
   if (!rt2_size(H) || !rt2_size(W)) return false;
   int tl = 0;
   RT2_DISPATCH(W, PLW, tl = PLW::TL);
-  return w <= tl * RT2_LPC && w >= 1;
+  return w <= tl * RT2_RLPC && w >= 1;
 }
 
 template <class K>
@@ -494,9 +501,9 @@ int ud_rt2_fwd(const float* dec, const float* x, float* rec, float2* Z, float* p
   int rc;
   RT2_DISPATCH(W, PLW, {
     auto k = rt2_rows_fwd_kernel<PLW>;
-    const size_t sm = sizeof(float2) * ((size_t)PLW::R1 * PLW::P + W + (size_t)RT2_LPC * PLW::LS + (size_t)RT2_LPC * w);
+    const size_t sm = sizeof(float2) * ((size_t)PLW::R1 * PLW::P + W + (size_t)RT2_RLPC * PLW::LS + (size_t)RT2_RLPC * w);
     if ((rc = rt2_set_smem(k, sm)) != UD_OK) return rc;
-    k<<<dim3(row_tiles, planes), PLW::TL * RT2_LPC, sm, stream>>>(dec, x, rec, Z, part_sp, twW, ytab, xtab, plane0, h, w, H,
+    k<<<dim3(row_tiles, planes), PLW::TL * RT2_RLPC, sm, stream>>>(dec, x, rec, Z, part_sp, twW, ytab, xtab, plane0, h, w, H,
                                                                     row_tiles, rt2_iters(H, row_tiles));
   });
   if ((rc = ud_check_launch("rt2_rows_fwd")) != UD_OK) return rc;
@@ -531,9 +538,9 @@ int ud_rt2_bwd(const float* dec, const float* x, const uint8_t* signs, const flo
   if ((rc = ud_check_launch("rt2_cols_bwd")) != UD_OK) return rc;
   RT2_DISPATCH(W, PLW, {
     auto k = rt2_rows_bwd_kernel<PLW>;
-    const size_t sm = sizeof(float2) * ((size_t)PLW::R1 * PLW::P + W + (size_t)RT2_LPC * PLW::LS + (size_t)RT2_LPC * w);
+    const size_t sm = sizeof(float2) * ((size_t)PLW::R1 * PLW::P + W + (size_t)RT2_RLPC * PLW::LS + (size_t)RT2_RLPC * w);
     if ((rc = rt2_set_smem(k, sm)) != UD_OK) return rc;
-    k<<<dim3(row_tiles, planes), PLW::TL * RT2_LPC, sm, stream>>>(dec, x, T, g_spatial, g_freq, g_dec, twW, ytab, xtab,
+    k<<<dim3(row_tiles, planes), PLW::TL * RT2_RLPC, sm, stream>>>(dec, x, T, g_spatial, g_freq, g_dec, twW, ytab, xtab,
                                                                     jtab, plane0, C, h, w, H, sp_scale, rt2_iters(H, row_tiles));
   });
   return ud_check_launch("rt2_rows_bwd");
