@@ -69,8 +69,21 @@ def test_mix(shape, dtype, cl):
           atol=(2e-2 if dtype == torch.bfloat16 else 1e-4) * float(ref[2].grad.abs()) + 1e-4)
 
 
+@pytest.mark.parametrize("own_fft", [False, True])
 @pytest.mark.parametrize("cl", [False, True])
-def test_sfconv_modules_reference_fixture(golden_ops, cl):
+def test_sfconv_modules_reference_fixture(golden_ops, cl, own_fft):
+    """own_fft: the fp32 path on this repo's transforms (ud_rfft2 / ud_irfft2 with their autograd adjoints) instead of
+    cuFFT -- same reference fixtures, same tolerances."""
+    from unidefense_b200.model import sfconv as SF
+    old = SF.USE_OWN_FFT
+    SF.USE_OWN_FFT = own_fft
+    try:
+        _sfconv_fixture_body(golden_ops, cl)
+    finally:
+        SF.USE_OWN_FFT = old
+
+
+def _sfconv_fixture_body(golden_ops, cl):
     from unidefense_b200.model.sfconv import SFConv2d, SFSamePadConv2d
     for c in golden_ops["sfconv"]:
         C, hw, s = c["x"].shape[1], c["x"].shape[-1], c["stride"]

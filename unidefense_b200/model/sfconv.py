@@ -39,6 +39,10 @@ USE_DFT_GEMM = os.environ.get("UD_SFCONV_DFT_GEMM", "1") != "0"
 # largest side evaluated as DFT-by-GEMM: 96 covers every SFConv layer of the shipped configs (95^2 at EB4@380 is the
 # biggest: with it on the GEMM path the step went 77.2 -> 74.0 ms on a B200; 64 was the round-1 setting)
 _DFT_MAX = int(os.environ.get("UD_SFCONV_DFT_MAX", "96"))
+# fp32 path on this repo's own transforms instead of cuFFT (opt-in): ud_rfft2 emits the cat([re, im], 1) planar spectrum
+# the 1x1 convolution consumes and ud_irfft2 takes it back, so the pack / unpack passes disappear as well; any plane size,
+# autograd through the kernels' adjoint modes.  Off by default: the library path is what the timings were taken on.
+USE_OWN_FFT = os.environ.get("UD_SFCONV_OWN_FFT", "0") == "1"
 _dft_cache = {}
 
 
@@ -105,6 +109,13 @@ def _sf_forward(x, spat, freq_conv, sf_coef, norm):
     size = x.shape[-2:]
     if _dft_gemm_ok(x, spat):
         return _sf_forward_gemm(x, spat, freq_conv, sf_coef, norm)
+    if USE_OWN_FFT and x.is_cuda and not torch.is_autocast_enabled():
+        from .. import ops
+        planar = freq_conv(ops.rfft2_cat(x.float().contiguous(), norm))
+        y = ops.irfft2_cat(planar.float().contiguous(), size, norm)
+        if tuple(y.shape[-2:]) != tuple(spat.shape[-2:]):
+            y = F.adaptive_avg_pool2d(y, spat.shape[-2:])
+        return ops.sf_mix(spat, y, sf_coef)
     if USE_GLUE_KERNELS and x.is_cuda:
         from .. import ops
         xf = x.to(dtype=torch.float32, memory_format=torch.contiguous_format)
