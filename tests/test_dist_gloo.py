@@ -147,3 +147,44 @@ def test_packed_reduction_without_a_process_group():
     got = PAR.reduce_scalars({"a_loss": torch.tensor(1.5), "b": 2.0})
     assert got == {"a_loss": 1.5, "b": 2.0} and PAR.reduce_scalars({}) == {}
     assert float(PAR.reduce_tensor(torch.tensor(3.0))) == 3.0
+
+
+def _flat_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from unidefense_b200 import parallel as PAR
+        torch.manual_seed(0)                                  # same weights on every rank
+        net = nn.Sequential(nn.Conv2d(3, 4, 3, padding=1), nn.ReLU(), nn.Conv2d(4, 2, 1, bias=False))
+        net[0].weight.data = net[0].weight.data.contiguous(memory_format=torch.channels_last)     # strided .grad views
+        net[2].weight.requires_grad_(True)
+        frozen = nn.Parameter(torch.ones(3), requires_grad=False)
+        fg = PAR.FlatGradients(list(net.parameters()) + [frozen])
+        assert fg.flat.numel() == sum(p.numel() for p in net.parameters()) and frozen.grad is None
+        g = torch.Generator().manual_seed(10 + rank)          # a different shard per rank
+        steps = []
+        for it in range(2):
+            fg.zero()
+            x = torch.randn(2 + rank, 3, 5, 5, generator=g)
+            net(x).square().mean().backward()                 # autograd accumulates straight into the flat buffer
+            local = [p.grad.clone() for p in net.parameters()]
+            fg.all_reduce()
+            steps.append(dict(local=local, reduced=[p.grad.clone() for p in net.parameters()], flat=fg.flat.clone()))
+        out[rank] = steps
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradients_average_over_two_ranks():
+    """FlatGradients == DDP's semantics (mean of the per-rank gradients), one all-reduce of one buffer; .grad views keep
+    the parameters' strides (channels_last weights) and survive zero() / repeated steps."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_flat_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for it in range(2):
+        a, b = out[0][it], out[1][it]
+        for la, lb, ra, rb in zip(a["local"], b["local"], a["reduced"], b["reduced"]):
+            torch.testing.assert_close(ra, (la + lb) / 2, rtol=1e-6, atol=1e-7)
+            assert torch.equal(ra, rb)
+        assert torch.equal(a["flat"], b["flat"])
+    assert out[0][0]["reduced"][0].is_contiguous(memory_format=torch.channels_last)

@@ -116,7 +116,11 @@ class FlatGradients:
 
     def all_reduce(self):
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:                                   # gloo (CPU tests) has no AVG
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat /= float(dist.get_world_size(self.group))
 
 
 class _SyncBNFunction(torch.autograd.Function):
