@@ -436,15 +436,24 @@ def frequency_style_transfer(content: Tensor, style: Tensor, lmda: Tensor) -> Te
     return torch.fft.irfft2(mix, s=(H, W), norm="ortho")
 
 
-def spatial_style_transfer(content: Tensor, style: Tensor, lmda: Tensor) -> Tensor:
-    """modules.py:59-76 (exact histogram matching); lmda [B,1,1]."""
+def spatial_style_transfer(content: Tensor, style: Tensor, lmda: Tensor, stable: bool = False) -> Tensor:
+    """modules.py:59-76 (exact histogram matching); lmda [B,1,1].  The reference sorts with torch.sort's default, which
+    leaves the order of EQUAL content values open; `stable=True` fixes it to pixel order -- the CUDA kernel's tie rule
+    (csrc/ud_style_sort.cu) -- so that planes with repeated values have one defined answer."""
     B, C, H, W = content.shape
     cf = content.reshape(B, C, -1)
-    _, idx = torch.sort(cf, dim=-1)
+    _, idx = torch.sort(cf, dim=-1, stable=stable)
     vs, _ = torch.sort(style.reshape(B, C, -1), dim=-1)
     inv = idx.argsort(-1)
     out = cf + (1 - lmda) * vs.gather(-1, inv) - (1 - lmda) * cf
     return out.view(B, C, H, W)
+
+
+def spectral_mask_filter(x: Tensor, mask: Tensor, norm="ortho") -> Tensor:
+    """irfft2(mask * rfft2(x)): the FFT2 + mask + IFFT2 composite of BASELINE.json configs[4]; the mask [N,H,W/2+1] is
+    shared by the channels of a sample as the dynamic filter's is (model/unidefense.py:135-145)."""
+    H, W = x.shape[-2:]
+    return torch.fft.irfft2(torch.fft.rfft2(x, norm=norm) * mask.unsqueeze(1), s=(H, W), norm=norm)
 
 
 def coral_stats(img: Tensor):

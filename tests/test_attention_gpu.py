@@ -153,7 +153,6 @@ def test_spectral_mask_filter_composite(shape):
     x = torch.randn(shape, generator=g)
     mask = torch.rand(N, H, W // 2 + 1, generator=g)
     y = ops.spectral_mask_filter(x.cuda(), mask.cuda())
-    want = torch.fft.irfft2(torch.fft.rfft2(x.double(), norm="ortho") * mask.double().unsqueeze(1), s=(H, W), norm="ortho")
-    close(y, want)
+    close(y, O.spectral_mask_filter(x.double(), mask.double()))
     with pytest.raises(ValueError):
         ops.spectral_mask_filter(x.cuda(), mask[:, :-1].cuda())

@@ -194,3 +194,23 @@ def test_recon_path_against_reference_model(golden_path):
     _, s2, f2 = O.recon_tail(d, x)
     (gd,) = torch.autograd.grad((s2 * gsp).sum() + (f2 * gfr).sum(), d)
     close(O.recon_tail_backward_closed_form(d.detach(), x, gsp, gfr), gd, rtol=1e-3, atol=1e-3 * float(gd.abs().max()))
+
+
+def test_stable_rank_matching_and_spectral_composite():
+    """The two oracle functions added for the round-2 kernels: the stable-sort variant equals the reference's on tie-free
+    planes (its fixtures) and resolves ties in pixel order; the FFT2 + mask + IFFT2 composite is the identity for an
+    all-ones mask and linear in the mask."""
+    import torch
+    g = torch.Generator().manual_seed(1)
+    content = torch.randn(2, 3, 9, 7, generator=g)
+    style = torch.randn(2, 3, 9, 7, generator=g)
+    lm = torch.rand(2, 1, 1, generator=g) / 2 + 0.5
+    torch.testing.assert_close(O.spatial_style_transfer(content, style, lm, stable=True), O.spatial_style_transfer(content, style, lm))
+    tied = torch.tensor([2.0, 1.0, 2.0, 1.0]).view(1, 1, 2, 2)
+    out = O.spatial_style_transfer(tied, torch.arange(4.0).view(1, 1, 2, 2), torch.zeros(1, 1, 1), stable=True)
+    assert out.flatten().tolist() == [2.0, 0.0, 3.0, 1.0]
+    x = torch.randn(2, 3, 10, 9, generator=g, dtype=torch.float64)
+    ones = torch.ones(2, 10, 5, dtype=torch.float64)
+    torch.testing.assert_close(O.spectral_mask_filter(x, ones), x)
+    m1, m2 = torch.rand(2, 10, 5, generator=g, dtype=torch.float64), torch.rand(2, 10, 5, generator=g, dtype=torch.float64)
+    torch.testing.assert_close(O.spectral_mask_filter(x, m1 + 2 * m2), O.spectral_mask_filter(x, m1) + 2 * O.spectral_mask_filter(x, m2))

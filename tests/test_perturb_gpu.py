@@ -100,9 +100,7 @@ def test_spatial_style_sort_kernel(shape):
     close(y.flatten(2).sort(-1).values, want.flatten(2).sort(-1).values, rtol=1e-6, atol=1e-6)
     assert float(((y.cpu() - want).abs() <= 1e-6 + 1e-6 * want.abs()).float().mean()) > 0.998
     # ... and pixel by pixel with the same formula evaluated with a STABLE sort, which is the kernel's tie rule
-    cf, lm3 = content.flatten(2), lm.view(-1, 1, 1)
-    inv = torch.argsort(torch.sort(cf, dim=-1, stable=True).indices, dim=-1)
-    stable = cf + (1 - lm3) * style.flatten(2).sort(-1).values.gather(-1, inv) - (1 - lm3) * cf
+    stable = O.spatial_style_transfer(content, style, lm.view(-1, 1, 1), stable=True).flatten(2)
     torch.testing.assert_close(y.flatten(2).cpu(), stable, rtol=0, atol=1e-6)
     # sorting sanity: lmda = 0 reproduces the style's multiset exactly, in the content's rank order
     y0 = ops.spatial_style_transfer(content.cuda(), style.cuda(), torch.zeros(shape[0]).cuda())
